@@ -1,0 +1,249 @@
+// Context, error plumbing, device matrices, lifecycle entry points of libmor_b200.so.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "internal.h"
+
+namespace mor {
+
+static thread_local std::string g_last_error;
+static Ctx g_ctx;
+static std::mutex g_mutex;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file,
+             line, what);
+    set_error(buf);
+    // clear the sticky-free error state so later calls report their own failures
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? MOR_ERR_NOMEM : MOR_ERR_CUDA;
+}
+
+Ctx& ctx() { return g_ctx; }
+
+int32_t require_ctx() {
+    if (!g_ctx.ready) {
+        // lazy default: device 0
+        return mor_b200_init(0);
+    }
+    MOR_CUDA(cudaSetDevice(g_ctx.device));
+    return MOR_OK;
+}
+
+int32_t DevBuf::alloc(size_t nbytes) {
+    release();
+    if (nbytes == 0) nbytes = 8;
+    cudaError_t e = cudaMalloc(&p, nbytes);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    }
+    bytes = nbytes;
+    return MOR_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+Timer::Timer(int slot_) : slot(slot_) {}
+Timer::~Timer() {
+    for (auto& s : spans) {
+        cudaEventDestroy(s.first);
+        cudaEventDestroy(s.second);
+    }
+}
+void Timer::start() {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, ctx().stream);
+    running = true;
+}
+void Timer::stop() {
+    if (!running) return;
+    cudaEventRecord(b, ctx().stream);
+    spans.emplace_back(a, b);
+    running = false;
+}
+void Timer::collect() {
+    for (auto& s : spans) {
+        cudaEventSynchronize(s.second);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) ctx().timings[slot] += ms;
+        cudaEventDestroy(s.first);
+        cudaEventDestroy(s.second);
+    }
+    spans.clear();
+}
+
+}  // namespace mor
+
+using namespace mor;
+
+extern "C" {
+
+int32_t mor_b200_version(void) { return MOR_B200_VERSION; }
+
+const char* mor_b200_last_error(void) { return g_last_error.c_str(); }
+
+int32_t mor_b200_init(int32_t device) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_ctx.ready && g_ctx.device == device) return MOR_OK;
+    MOR_ARG(device >= 0, "mor_b200_init: device must be >= 0");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("mor_b200_init: no CUDA device available (this library has no CPU fallback)");
+        return MOR_ERR_CUDA;
+    }
+    MOR_ARG(device < count, "mor_b200_init: device ordinal out of range");
+    MOR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MOR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("mor_b200_init: libmor_b200 is built for sm_100a (B200) only");
+        return MOR_ERR_CUDA;
+    }
+    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+    MOR_CUDA(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
+    g_ctx.stream = g_ctx.own_stream;
+    g_ctx.device = device;
+    g_ctx.num_sms = prop.multiProcessorCount;
+    g_ctx.ready = true;
+    return MOR_OK;
+}
+
+int32_t mor_b200_shutdown(void) {
+    mor_b200_comm_destroy();
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        cudaStreamSynchronize(g_ctx.stream);
+        if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+        g_ctx.own_stream = nullptr;
+        g_ctx.stream = nullptr;
+        g_ctx.ready = false;
+    }
+    return MOR_OK;
+}
+
+int32_t mor_b200_set_stream(void* cuda_stream) {
+    MOR_TRY(require_ctx());
+    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
+    return MOR_OK;
+}
+
+int32_t mor_b200_sync(void) {
+    MOR_TRY(require_ctx());
+    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+int32_t mor_b200_last_timings(double* ms, int32_t n) {
+    MOR_ARG(ms != nullptr && n >= 0, "mor_b200_last_timings: bad arguments");
+    for (int i = 0; i < n; ++i) ms[i] = i < MOR_T_NSLOTS ? g_ctx.timings[i] : 0.0;
+    return MOR_OK;
+}
+
+int64_t mor_b200_launch_count(int32_t reset) {
+    int64_t v = g_ctx.launches;
+    if (reset) g_ctx.launches = 0;
+    return v;
+}
+
+// ---- device matrices ----------------------------------------------------------------------
+int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
+    MOR_ARG(out != nullptr && m >= 0 && n >= 0, "mor_b200_mat_alloc: bad arguments");
+    MOR_TRY(require_ctx());
+    int64_t ld = (m + 1) & ~int64_t(1);  // even: 16-byte aligned columns (TMA / v2 loads)
+    if (ld == 0) ld = 2;
+    size_t bytes = (size_t)ld * (size_t)(n > 0 ? n : 1) * sizeof(double);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(matrix)", __FILE__, __LINE__);
+    if (ld != m) {  // keep the pad row finite
+        MOR_CUDA(cudaMemsetAsync(p, 0, bytes, g_ctx.stream));
+    }
+    mor_mat_s* a = new mor_mat_s;
+    a->p = (double*)p;
+    a->m = m;
+    a->n = n;
+    a->ld = ld;
+    a->owned = true;
+    *out = a;
+    return MOR_OK;
+}
+
+int32_t mor_b200_mat_wrap(void* device_ptr, int64_t m, int64_t n, int64_t ld, mor_mat_t* out) {
+    MOR_ARG(out != nullptr && device_ptr != nullptr && m >= 0 && n >= 0 && ld >= m && ld >= 1,
+            "mor_b200_mat_wrap: bad arguments");
+    MOR_TRY(require_ctx());
+    mor_mat_s* a = new mor_mat_s;
+    a->p = (double*)device_ptr;
+    a->m = m;
+    a->n = n;
+    a->ld = ld;
+    a->owned = false;
+    *out = a;
+    return MOR_OK;
+}
+
+int32_t mor_b200_mat_free(mor_mat_t a) {
+    if (!a) return MOR_OK;
+    if (a->owned && a->p) {
+        if (g_ctx.ready) {
+            cudaSetDevice(g_ctx.device);
+            cudaStreamSynchronize(g_ctx.stream);
+        }
+        cudaFree(a->p);
+    }
+    delete a;
+    return MOR_OK;
+}
+
+int32_t mor_b200_mat_info(mor_mat_t a, int64_t* m, int64_t* n, int64_t* ld, void** device_ptr) {
+    MOR_ARG(a != nullptr, "mor_b200_mat_info: null matrix");
+    if (m) *m = a->m;
+    if (n) *n = a->n;
+    if (ld) *ld = a->ld;
+    if (device_ptr) *device_ptr = a->p;
+    return MOR_OK;
+}
+
+int32_t mor_b200_mat_upload(mor_mat_t a, const double* host, int64_t ldh) {
+    MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_upload: bad arguments");
+    MOR_TRY(require_ctx());
+    if (a->m == 0 || a->n == 0) return MOR_OK;
+    MOR_CUDA(cudaMemcpy2DAsync(a->p, (size_t)a->ld * 8, host, (size_t)ldh * 8, (size_t)a->m * 8,
+                               (size_t)a->n, cudaMemcpyHostToDevice, g_ctx.stream));
+    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+int32_t mor_b200_mat_download(mor_mat_t a, double* host, int64_t ldh) {
+    MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_download: bad arguments");
+    MOR_TRY(require_ctx());
+    if (a->m == 0 || a->n == 0) return MOR_OK;
+    MOR_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, a->p, (size_t)a->ld * 8, (size_t)a->m * 8,
+                               (size_t)a->n, cudaMemcpyDeviceToHost, g_ctx.stream));
+    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_row0, double param,
+                       int64_t iparam) {
+    MOR_ARG(a != nullptr && global_row0 >= 0, "mor_b200_synth: bad arguments");
+    MOR_TRY(require_ctx());
+    MOR_TRY(synth_fill(a->p, a->m, a->n, a->ld, kind, seed, global_row0, param, iparam));
+    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// DEIM interpolation-index selection -- replaces the body of deim_interpolation_indices,
+// /root/reference/src/deim.jl:9-28.
+//
+// Per greedy step l (reference lines in brackets):
+//   deim_step_kernel    r_i = |u_l[i] - sum_j U[i,j] c_j| fused with the abs-argmax   [l.22-24]
+//                       -- one streaming pass over columns 1..l of the basis, HBM-bound.
+//   deim_local_kernel   reduce the per-CTA candidates, gather the winner's basis row [l.16-20]
+//   (ncclAllGather)     (value, global index, row) of every rank                  (multi-GPU)
+//   deim_update_kernel  pick the global winner (value, then LOWEST global index = Julia's
+//                       first-index tie-break, NaN maximal), append its row to P'U and
+//                       solve (P'U) c = P'u_{l+1} for the next step                    [l.21]
+//
+// The small solve keeps the LU factors of P'U incrementally: P'U grows by one row and one
+// column per step and the greedy choice IS partial pivoting (the pivot is the residual of
+// largest magnitude), so the bordered Doolittle update reproduces dgetrf's factorisation
+// without row exchanges.  Z = inv(U-factor) is kept explicitly so every phase is a parallel
+// dot product instead of a 255-long dependent substitution chain.
+#include <climits>
+#include <cstdint>
+
+#include "internal.h"
+
+namespace mor {
+
+struct Cand {
+    double val;
+    long long idx;
+};
+
+#define MOR_IDX_NONE LLONG_MAX
+
+// true when candidate a beats candidate b (Julia argmax semantics + lowest-index tie-break)
+__device__ __forceinline__ bool cand_better(double va, long long ia, double vb, long long ib) {
+    if (ia == MOR_IDX_NONE) return false;
+    if (ib == MOR_IDX_NONE) return true;
+    const bool na = va != va, nb = vb != vb;
+    if (na | nb) return (na & nb) ? (ia < ib) : na;
+    return (va > vb) || (va == vb && ia < ib);
+}
+
+__device__ __forceinline__ void cand_warp_reduce(double& v, long long& i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        long long oi = __shfl_xor_sync(0xffffffffu, i, off);
+        if (cand_better(ov, oi, v, i)) {
+            v = ov;
+            i = oi;
+        }
+    }
+}
+
+// block-wide reduce; result valid in thread 0
+template <int NWARPS>
+__device__ __forceinline__ void cand_block_reduce(double& v, long long& i, double* sv, long long* si) {
+    cand_warp_reduce(v, i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sv[warp] = v;
+        si[warp] = i;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < NWARPS ? sv[lane] : -1.0;
+        i = lane < NWARPS ? si[lane] : MOR_IDX_NONE;
+        cand_warp_reduce(v, i);
+    }
+}
+
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream1(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// running best of one thread; rows arrive in ascending order so ties keep the earlier row
+__device__ __forceinline__ void cand_take(double& bv, long long& bi, double v, long long idx) {
+    if (!(bv != bv) && ((v != v) || v > bv)) {
+        bv = v;
+        bi = idx;
+    }
+}
+
+constexpr int DEIM_THREADS = 256;
+
+// Fused residual + abs-argmax over this rank's rows.  l = number of previous columns.
+// VEC: 16-byte loads (needs 16B-aligned base and even ld).  Each CTA walks chunks of
+// 2*R*256 consecutive rows; for every column the CTA reads one contiguous 4*R KB run.
+template <int R, bool VEC>
+__global__ void __launch_bounds__(DEIM_THREADS)
+deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
+                 const double* __restrict__ cg, int64_t row_offset, Cand* __restrict__ out) {
+    __shared__ double sc[1024];
+    __shared__ double sv[DEIM_THREADS / 32];
+    __shared__ long long si[DEIM_THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < l; j += DEIM_THREADS) sc[j] = cg[j];
+    __syncthreads();
+
+    const int64_t CH = 2 * R * DEIM_THREADS;
+    const int64_t nchunks = (m + CH - 1) / CH;
+    const double* __restrict__ ul = U + (int64_t)l * ld;
+    double bv = -1.0;
+    long long bi = MOR_IDX_NONE;
+
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t c0 = chunk * CH;
+        if (c0 + CH <= m) {
+            if (VEC) {
+                double2 acc[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = make_double2(0.0, 0.0);
+                const double* p = U + c0 + 2 * tid;
+                int j = 0;
+                // two columns per trip: 2*R independent 16-byte loads in flight per thread
+                for (; j + 2 <= l; j += 2) {
+                    double2 v0[R], v1[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) v0[r] = ld_stream2(p + r * (2 * DEIM_THREADS));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) v1[r] = ld_stream2(p + ld + r * (2 * DEIM_THREADS));
+                    const double ca = sc[j], cb = sc[j + 1];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r].x = fma(v0[r].x, ca, acc[r].x);
+                        acc[r].y = fma(v0[r].y, ca, acc[r].y);
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r].x = fma(v1[r].x, cb, acc[r].x);
+                        acc[r].y = fma(v1[r].y, cb, acc[r].y);
+                    }
+                    p += 2 * ld;
+                }
+                if (j < l) {
+                    const double cj = sc[j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double2 v = ld_stream2(p + r * (2 * DEIM_THREADS));
+                        acc[r].x = fma(v.x, cj, acc[r].x);
+                        acc[r].y = fma(v.y, cj, acc[r].y);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int64_t row = c0 + 2 * tid + r * (2 * DEIM_THREADS);
+                    const double2 u = ld_stream2(ul + row);
+                    cand_take(bv, bi, fabs(u.x - acc[r].x), row_offset + row);
+                    cand_take(bv, bi, fabs(u.y - acc[r].y), row_offset + row + 1);
+                }
+            } else {
+                double acc[2 * R];
+#pragma unroll
+                for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0;
+                const double* p = U + c0 + tid;
+#pragma unroll 2
+                for (int j = 0; j < l; ++j) {
+                    const double cj = sc[j];
+#pragma unroll
+                    for (int r = 0; r < 2 * R; ++r)
+                        acc[r] = fma(ld_stream1(p + r * DEIM_THREADS), cj, acc[r]);
+                    p += ld;
+                }
+#pragma unroll
+                for (int r = 0; r < 2 * R; ++r) {
+                    const int64_t row = c0 + tid + r * DEIM_THREADS;
+                    cand_take(bv, bi, fabs(ld_stream1(ul + row) - acc[r]), row_offset + row);
+                }
+            }
+        } else {  // ragged last chunk
+            for (int64_t row = c0 + tid; row < m; row += DEIM_THREADS) {
+                double acc = 0.0;
+                const double* p = U + row;
+                for (int j = 0; j < l; ++j) acc = fma(p[(int64_t)j * ld], sc[j], acc);
+                cand_take(bv, bi, fabs(ul[row] - acc), row_offset + row);
+            }
+        }
+    }
+    cand_block_reduce<DEIM_THREADS / 32>(bv, bi, sv, si);
+    if (tid == 0) {
+        out[blockIdx.x].val = bv;
+        out[blockIdx.x].idx = bi;
+    }
+}
+
+// Reduce the per-CTA candidates of this rank and gather the winner's basis row:
+// send = [value, bits(global index), U[idx, 0..k)]
+__global__ void __launch_bounds__(1024)
+deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __restrict__ U, int64_t ld,
+                  int64_t row_offset, int k, double* __restrict__ send) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    __shared__ long long widx;
+    double bv = -1.0;
+    long long bi = MOR_IDX_NONE;
+    for (int t = threadIdx.x; t < ncand; t += 1024) {
+        const double v = cands[t].val;
+        const long long i = cands[t].idx;
+        if (cand_better(v, i, bv, bi)) {
+            bv = v;
+            bi = i;
+        }
+    }
+    cand_block_reduce<32>(bv, bi, sv, si);
+    if (threadIdx.x == 0) {
+        widx = bi;
+        send[0] = bv;
+        send[1] = __longlong_as_double(bi);
+    }
+    __syncthreads();
+    const long long g = widx;
+    for (int j = threadIdx.x; j < k; j += 1024)
+        send[2 + j] = (g == MOR_IDX_NONE) ? 0.0 : U[(g - row_offset) + (int64_t)j * ld];
+}
+
+__device__ __forceinline__ double warp_sum(double s) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+}
+
+// Replicated on every rank: choose the global winner, append its row to W = P'U (row i),
+// extend the LU factors (L row i, U-factor row i, Z column i) and compute the coefficient
+// vector c (length i+1) of the NEXT step.  All k x k arrays are row-major with stride k.
+__global__ void __launch_bounds__(1024)
+deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k, double* __restrict__ Wm,
+                   double* __restrict__ Uf, double* __restrict__ Lm, double* __restrict__ Z,
+                   double* __restrict__ c, long long* __restrict__ idx_out, int* __restrict__ status) {
+    __shared__ double w[1024], ell[1024], ucol[1024], y[1024];
+    __shared__ int win_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = k + 2;
+    if (tid == 0) {
+        int win = 0;
+        double bv = -1.0;
+        long long bi = MOR_IDX_NONE;
+        for (int r = 0; r < nranks; ++r) {
+            const double v = gathered[(size_t)r * stride];
+            const long long ix = __double_as_longlong(gathered[(size_t)r * stride + 1]);
+            if (cand_better(v, ix, bv, bi)) {
+                bv = v;
+                bi = ix;
+                win = r;
+            }
+        }
+        win_s = win;
+        idx_out[i] = bi + 1;  // 1-based, like Julia
+    }
+    __syncthreads();
+    const double* src = gathered + (size_t)win_s * stride + 2;
+    for (int j = tid; j < k; j += 1024) {
+        const double v = src[j];
+        w[j] = v;
+        Wm[(size_t)i * k + j] = v;
+    }
+    __syncthreads();
+    // L row: ell = w[0:i] * Z   (Z = inv(Uf[0:i,0:i]), upper triangular)
+    for (int j = tid; j < i; j += 1024) {
+        double s = 0.0;
+        for (int t = 0; t <= j; ++t) s = fma(w[t], Z[(size_t)t * k + j], s);
+        ell[j] = s;
+        Lm[(size_t)i * k + j] = s;
+    }
+    __syncthreads();
+    // U-factor row i:  Uf[i][j] = w[j] - sum_{t<i} ell[t] * Uf[t][j],  j >= i
+    for (int j = i + tid; j < k; j += 1024) {
+        double s = w[j];
+        for (int t = 0; t < i; ++t) s = fma(-ell[t], Uf[(size_t)t * k + j], s);
+        Uf[(size_t)i * k + j] = s;
+    }
+    for (int t = tid; t < i; t += 1024) ucol[t] = Uf[(size_t)t * k + i];
+    __syncthreads();
+    const double pivot = Uf[(size_t)i * k + i];
+    if (tid == 0 && pivot == 0.0 && i < k - 1 && *status == 0) *status = i + 1;
+    // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot
+    for (int r = warp; r < i; r += 32) {
+        double s = 0.0;
+        for (int t = r + lane; t < i; t += 32) s = fma(Z[(size_t)r * k + t], ucol[t], s);
+        s = warp_sum(s);
+        if (lane == 0) Z[(size_t)r * k + i] = -s / pivot;
+    }
+    if (tid == 0) Z[(size_t)i * k + i] = 1.0 / pivot;
+    if (i + 1 >= k) return;
+    for (int t = tid; t <= i; t += 1024) y[t] = Uf[(size_t)t * k + i + 1];
+    __syncthreads();
+    // c = Z[0:i+1, 0:i+1] * y   (y = inv(L) * P'u_{l+1} is column i+1 of the U-factor)
+    for (int r = warp; r <= i; r += 32) {
+        double s = 0.0;
+        for (int t = r + lane; t <= i; t += 32) s = fma(Z[(size_t)r * k + t], y[t], s);
+        s = warp_sum(s);
+        if (lane == 0) c[r] = s;
+    }
+}
+
+int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host) {
+    Ctx& cx = ctx();
+    MOR_ARG(B != nullptr && idx_host != nullptr, "deim_interpolation_indices: null pointer");
+    MOR_ARG(k >= 1 && k <= 1024, "deim_interpolation_indices: number of basis columns must be in 1..1024");
+    MOR_ARG(m >= 0 && ld >= (m > 0 ? m : 1), "deim_interpolation_indices: bad m / ld");
+    for (double& t : cx.timings) t = 0.0;
+
+    std::vector<int64_t> all_m;
+    MOR_TRY(comm_allgather_i64(m, all_m));
+    int64_t row_offset = 0, m_global = 0;
+    for (int r = 0; r < cx.nranks; ++r) {
+        if (r < cx.rank) row_offset += all_m[r];
+        m_global += all_m[r];
+    }
+    MOR_ARG(m_global >= 1, "deim_interpolation_indices: empty basis");
+
+    constexpr int R = 4;
+    const int64_t CH = 2 * R * DEIM_THREADS;
+    int64_t nchunks = (m + CH - 1) / CH;
+    int grid = (int)(nchunks < (int64_t)cx.num_sms * 8 ? nchunks : (int64_t)cx.num_sms * 8);
+    if (grid < 1) grid = 1;
+    const bool vec = ((uintptr_t)B % 16 == 0) && (ld % 2 == 0);
+
+    const size_t kk = (size_t)k * k;
+    DevBuf state, cands, xfer;
+    // state: Wm, Uf, Lm, Z (k*k each), c (k), idx (k int64), status
+    MOR_TRY(state.alloc(sizeof(double) * (4 * kk + k) + sizeof(long long) * k + 16));
+    MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
+    MOR_TRY(xfer.alloc(sizeof(double) * (size_t)(k + 2) * (size_t)(cx.nranks + 1)));
+    MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
+    double* Wm = state.as<double>();
+    double* Uf = Wm + kk;
+    double* Lm = Uf + kk;
+    double* Z = Lm + kk;
+    double* c = Z + kk;
+    long long* idx_d = reinterpret_cast<long long*>(c + k);
+    int* status_d = reinterpret_cast<int*>(idx_d + k);
+    double* send = xfer.as<double>();
+    double* gathered = cx.nranks > 1 ? send + (k + 2) : send;
+
+    Timer t_total(MOR_T_TOTAL), t_step(MOR_T_DEIM_STEP), t_tail(MOR_T_DEIM_TAIL);
+    t_total.start();
+    for (int i = 0; i < (int)k; ++i) {
+        t_step.start();
+        if (vec)
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+        else
+            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+        t_step.stop();
+        t_tail.start();
+        deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send);
+        if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)(k + 2)));
+        deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, i, (int)k, Wm, Uf, Lm, Z, c, idx_d, status_d);
+        t_tail.stop();
+        count_launch(3);
+    }
+    t_total.stop();
+    MOR_CUDA(cudaGetLastError());
+    std::vector<long long> idx_h((size_t)k);
+    int status_h = 0;
+    MOR_CUDA(cudaMemcpyAsync(idx_h.data(), idx_d, sizeof(long long) * (size_t)k, cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(&status_h, status_d, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaStreamSynchronize(cx.stream));
+    t_total.collect();
+    t_step.collect();
+    t_tail.collect();
+    for (int64_t i = 0; i < k; ++i) idx_host[i] = (int64_t)idx_h[(size_t)i];
+    if (status_h != 0) {
+        set_error("deim_interpolation_indices: P'U is exactly singular at step " + std::to_string(status_h + 1) +
+                  " (SingularException in the reference)");
+        return MOR_ERR_SINGULAR;
+    }
+    return MOR_OK;
+}
+
+}  // namespace mor
+
+using namespace mor;
+
+extern "C" {
+
+int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {
+    MOR_ARG(B != nullptr, "mor_b200_deim_indices_dev: null matrix");
+    MOR_TRY(require_ctx());
+    return deim_indices_device(B->p, B->m, B->n, B->ld, idx_out);
+}
+
+int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out) {
+    MOR_ARG(B != nullptr && idx_out != nullptr, "mor_b200_deim_indices: null pointer");
+    MOR_ARG(m >= 0 && k >= 1 && ldb >= (m > 0 ? m : 1), "mor_b200_deim_indices: bad dimensions");
+    MOR_TRY(require_ctx());
+    mor_mat_t d = nullptr;
+    MOR_TRY(mor_b200_mat_alloc(m, k, &d));
+    int32_t st = mor_b200_mat_upload(d, B, ldb);
+    if (st == MOR_OK) st = deim_indices_device(d->p, d->m, d->n, d->ld, idx_out);
+    mor_b200_mat_free(d);
+    return st;
+}
+
+}  // extern "C"

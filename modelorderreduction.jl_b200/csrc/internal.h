@@ -1,0 +1,128 @@
+// Internal declarations shared by the translation units of libmor_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mor_b200.h"
+
+namespace mor {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const std::string& msg);
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MOR_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return ::mor::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define MOR_TRY(call)                    \
+    do {                                 \
+        int32_t s__ = (call);            \
+        if (s__ != MOR_OK) return s__;   \
+    } while (0)
+#define MOR_ARG(cond, msg)               \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::mor::set_error(msg);       \
+            return MOR_ERR_ARG;          \
+        }                                \
+    } while (0)
+
+// ---- context: one per process (= per GPU rank) ------------------------------------------
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;      // the stream all work is enqueued on
+    cudaStream_t own_stream = nullptr;  // created by init
+    void* comm = nullptr;               // ncclComm_t
+    int rank = 0, nranks = 1;
+    double timings[MOR_T_NSLOTS] = {0};
+    int64_t launches = 0;
+};
+Ctx& ctx();
+int32_t require_ctx();
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// RAII device buffer (freed with cudaFree on destruction)
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int32_t alloc(size_t nbytes);
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// CUDA-event stopwatch accumulating into ctx().timings[slot]
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int slot;
+    bool running = false;
+    explicit Timer(int slot_);
+    ~Timer();
+    void start();
+    void stop();  // records; elapsed is collected by collect()
+    void collect();  // synchronises on b and adds to the slot
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+};
+
+}  // namespace mor
+
+// ---- matrices ---------------------------------------------------------------------------
+struct mor_mat_s {
+    double* p = nullptr;
+    int64_t m = 0, n = 0, ld = 0;
+    bool owned = false;
+};
+
+namespace mor {
+
+// ---- collectives (nccl.cpp; NCCL is dlopen'ed on first use) -------------------------------
+int32_t comm_allreduce_sum(double* buf, size_t count);
+int32_t comm_allgather(const void* send, void* recv, size_t bytes_per_rank);
+int32_t comm_allgather_i64(int64_t mine, std::vector<int64_t>& all);  // host-visible
+
+// ---- synthetic inputs (synth.cu) ----------------------------------------------------------
+int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, uint64_t seed,
+                   int64_t row0, double param, int64_t iparam);
+int32_t fill_normal(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0,
+                    double scale);
+
+// ---- DEIM (deim.cu) -------------------------------------------------------------------------
+int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host);
+
+// ---- tall-skinny GEMMs on DMMA (gemm_tn.cu / gemm_nn.cu) -----------------------------------
+// C (p x q, ldc, column-major, both triangles when A == B) = A' * B, A: m x p, B: m x q.
+int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m,
+                double* C, int ldc);
+// Y (m x q) = X (m x n) * W (n x q).  Wt is W TRANSPOSED, i.e. q x n column-major ... see .cu
+// upper != 0: W is upper triangular (W[i][j] = 0 for i > j) and Y may alias X (in place).
+int32_t gemm_nn(const double* X, int64_t ldx, int n, const double* W, int ldw, int q, int64_t m,
+                double* Y, int64_t ldy, int upper);
+
+// ---- small dense kernels (small.cu) and Jacobi SVD (jacobi.cu) -------------------------------
+struct CholInfo {
+    double delta_f;   // ||G_s - I||_F of the scaled Gram matrix
+    double shift;     // shift finally used (0 if none)
+    int ok;
+};
+int32_t small_scale_chol(double* G, int n, int ld, double* D, double* Rs, CholInfo* info);
+int32_t small_trinv_upper(const double* R, int n, int ld, double* Rinv);
+int32_t small_gemm(bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda,
+                   const double* B, int ldb, double beta, double* C, int ldc);
+// One-sided Jacobi on the columns of A (rows x n, ld).  On return the columns are
+// orthogonal, sorted by decreasing norm; sigma[j] = ||A(:,j)||.  If J != nullptr it
+// receives the accumulated rotations (n x n, ld = ldj), A_in * J = A_out.
+int32_t jacobi_svd(double* A, int rows, int n, int ld, double* J, int ldj, double* sigma,
+                   int* sweeps_out);
+
+// ---- POD driver (pod.cu) ---------------------------------------------------------------------
+}  // namespace mor

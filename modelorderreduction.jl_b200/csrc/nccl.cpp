@@ -1,0 +1,175 @@
+// NCCL plumbing for the row-sharded (one process per GPU) mode.
+//
+// NCCL is loaded with dlopen on first use so that (a) a single-GPU user needs no NCCL at
+// all and (b) inside a torch process the library binds to the libnccl.so.2 torch already
+// mapped instead of dragging in a second copy.  Only the exchange steps of SURVEY.md
+// section 8e go through here: the n x n Gram all-reduce of the POD passes and the
+// (value, index, row) all-gather of every DEIM step.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "internal.h"
+
+namespace mor {
+
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+int32_t load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl.handle) return MOR_OK;
+    const char* override_path = getenv("MOR_B200_NCCL_LIB");
+    const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        if (!nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+        return MOR_ERR_CUDA;
+    }
+#define LOAD(field, sym)                                             \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, sym)); \
+    if (!g_nccl.field) {                                             \
+        set_error(std::string("NCCL symbol missing: ") + sym);       \
+        dlclose(h);                                                  \
+        return MOR_ERR_CUDA;                                         \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    g_nccl.handle = h;
+    return MOR_OK;
+}
+
+int32_t nccl_fail(ncclResult_t r, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "NCCL error %d (%s) in %s", (int)r,
+             g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what);
+    set_error(buf);
+    return MOR_ERR_CUDA;
+}
+}  // namespace
+
+int32_t comm_allreduce_sum(double* buf, size_t count) {
+    Ctx& c = ctx();
+    if (c.nranks <= 1 || count == 0) return MOR_OK;
+    ncclResult_t r =
+        g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)c.comm, c.stream);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+    return MOR_OK;
+}
+
+int32_t comm_allgather(const void* send, void* recv, size_t bytes_per_rank) {
+    Ctx& c = ctx();
+    if (c.nranks <= 1) {
+        if (send != recv) MOR_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, c.stream));
+        return MOR_OK;
+    }
+    ncclResult_t r =
+        g_nccl.AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)c.comm, c.stream);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
+    return MOR_OK;
+}
+
+int32_t comm_allgather_i64(int64_t mine, std::vector<int64_t>& all) {
+    Ctx& c = ctx();
+    all.assign((size_t)c.nranks, 0);
+    if (c.nranks <= 1) {
+        all[0] = mine;
+        return MOR_OK;
+    }
+    DevBuf d;
+    MOR_TRY(d.alloc(sizeof(int64_t) * (size_t)(c.nranks + 1)));
+    int64_t* dp = d.as<int64_t>();
+    MOR_CUDA(cudaMemcpyAsync(dp + c.nranks, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    MOR_TRY(comm_allgather(dp + c.nranks, dp, sizeof(int64_t)));
+    MOR_CUDA(cudaMemcpyAsync(all.data(), dp, sizeof(int64_t) * (size_t)c.nranks, cudaMemcpyDeviceToHost,
+                             c.stream));
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    return MOR_OK;
+}
+
+}  // namespace mor
+
+using namespace mor;
+
+extern "C" {
+
+int32_t mor_b200_comm_unique_id(void* id128) {
+    MOR_ARG(id128 != nullptr, "mor_b200_comm_unique_id: null buffer");
+    MOR_TRY(load_nccl());
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+    memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return MOR_OK;
+}
+
+int32_t mor_b200_comm_init(int32_t rank, int32_t nranks, const void* id128) {
+    MOR_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "mor_b200_comm_init: bad rank/nranks");
+    MOR_TRY(require_ctx());
+    Ctx& c = ctx();
+    if (c.comm) mor_b200_comm_destroy();
+    if (nranks == 1) {
+        c.rank = 0;
+        c.nranks = 1;
+        return MOR_OK;
+    }
+    MOR_ARG(id128 != nullptr, "mor_b200_comm_init: null unique id");
+    MOR_TRY(load_nccl());
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitRank");
+    c.comm = comm;
+    c.rank = rank;
+    c.nranks = nranks;
+    return MOR_OK;
+}
+
+int32_t mor_b200_comm_info(int32_t* rank, int32_t* nranks) {
+    if (rank) *rank = ctx().rank;
+    if (nranks) *nranks = ctx().nranks;
+    return MOR_OK;
+}
+
+int32_t mor_b200_comm_destroy(void) {
+    Ctx& c = ctx();
+    if (c.comm && g_nccl.CommDestroy) {
+        if (c.ready) {
+            cudaSetDevice(c.device);
+            cudaStreamSynchronize(c.stream);
+        }
+        g_nccl.CommDestroy((ncclComm_t)c.comm);
+    }
+    c.comm = nullptr;
+    c.rank = 0;
+    c.nranks = 1;
+    return MOR_OK;
+}
+
+}  // extern "C"

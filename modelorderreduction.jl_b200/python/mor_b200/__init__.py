@@ -1,0 +1,10 @@
+"""mor_b200 -- host-side mirror of ModelOrderReduction.jl's POD/DEIM numeric API over
+libmor_b200.so (hand-written sm_100a CUDA).  Same names and argument meaning as the
+reference: POD, SVD, TSVD, RSVD, reduce (= `reduce!`), deim_interpolation_indices."""
+from . import _lib
+from ._lib import MorError, SingularError
+from .deim import deim_interpolation_indices
+from .pod import POD, RSVD, SVD, TSVD, determine_truncation, errorhandle, reduce, reduce_bang
+
+__all__ = ["POD", "SVD", "TSVD", "RSVD", "reduce", "reduce_bang", "deim_interpolation_indices",
+           "determine_truncation", "errorhandle", "MorError", "SingularError"]

@@ -1,0 +1,341 @@
+"""CPU oracle for the POD / DEIM numeric hot path of SciML/ModelOrderReduction.jl.
+
+TEST INFRASTRUCTURE ONLY.  This module is the checker, never the product: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  The shipped path (``libmor_b200.so`` and the
+``mor_b200`` host mirror) never calls into ``oracle/``.
+
+PARITY UNPINNED BY THE REFERENCE: Julia is not installed in the build image and the
+reference's tests (``test/interface.jl``, ``test/DataReduction.jl``, ``test/deim.jl``)
+assert only shapes and ranges on this path, never a numeric value.
+The oracle is therefore pinned against (i) the analytic answers of the reference's own
+fixtures (``[3 0;0 1]``: s=[3,1], renergy .75/.5), (ii) the reference's range assertions,
+and (iii) the LAPACK routines Julia itself dispatches to (``dgesdd``, ``dgetrf/dgetrs``,
+``dgemv``), called here through scipy's OpenBLAS.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+Indices returned by :func:`deim_interpolation_indices` are 1-based, like Julia's.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import scipy.linalg as sla
+
+Array = np.ndarray
+Snapshots = Union[np.ndarray, Sequence[np.ndarray]]
+
+
+# --------------------------------------------------------------------------------------
+# Backend tags -- src/Types.jl:61-124
+# --------------------------------------------------------------------------------------
+@dataclass
+class SVD:
+    """src/Types.jl:61-70 -- dense SVD backend; kwargs forwarded to LinearAlgebra.svd."""
+    kwargs: dict = field(default_factory=dict)
+
+
+@dataclass
+class TSVD:
+    """src/Types.jl:86-95 -- truncated SVD backend (TSVD.jl)."""
+    kwargs: dict = field(default_factory=dict)
+
+
+@dataclass
+class RSVD:
+    """src/Types.jl:119-124 -- randomized SVD backend; ``p`` = oversampling (default 0)."""
+    p: int = 0
+
+
+# --------------------------------------------------------------------------------------
+# matricize / error handling -- src/DataReduction/POD.jl:4-6, src/ErrorHandle.jl:1-18
+# --------------------------------------------------------------------------------------
+def is_vov(snaps: Snapshots) -> bool:
+    return not isinstance(snaps, np.ndarray)
+
+
+def matricize(vov: Sequence[np.ndarray]) -> Array:
+    """POD.jl:4-6 -- ``reduce(hcat, VoV)``: n vectors of length m -> m x n matrix."""
+    return np.asfortranarray(np.stack([np.asarray(v, dtype=np.float64) for v in vov], axis=1))
+
+
+def errorhandle(snaps: Snapshots, nmodes: int, max_energy: float, min_nmodes: int,
+                max_nmodes: int) -> None:
+    """ErrorHandle.jl:1-18 -- the four ``@assert``s (AssertionError, like Julia)."""
+    if is_vov(snaps):
+        m, n = len(snaps[0]), len(snaps)          # ErrorHandle.jl:13-14
+    else:
+        m, n = snaps.shape                         # ErrorHandle.jl:2-3
+    assert m > 1, "State vector is expected to be vector valued."
+    s = min(m, n)
+    assert 0 < nmodes <= s, f"Number of modes should be in {{1,2,...,{s}}}."
+    assert min_nmodes <= max_nmodes, \
+        "Minimum number of modes must lie below maximum number of modes"
+    assert 0.0 <= max_energy <= 1.0, "Maximum relative energy must be in [0,1]"
+
+
+# --------------------------------------------------------------------------------------
+# POD problem record -- POD.jl:79-119
+# --------------------------------------------------------------------------------------
+class POD:
+    """POD.jl:79-119.  ``POD(snaps, k)`` is the positional form (l.111-118: energy
+    truncation disabled, min=max=nmodes=k); ``POD(snaps, min_renergy=..)`` the keyword
+    form (l.91-110).  Quirk kept: the keyword default ``max_nmodes = length(snaps[1])``
+    is 1 for a Matrix (``snaps[1]`` is a scalar) and m for a vector of vectors."""
+
+    def __init__(self, snaps: Snapshots, nmodes: Optional[int] = None, *,
+                 min_renergy: float = 1.0, min_nmodes: int = 1,
+                 max_nmodes: Optional[int] = None):
+        if nmodes is not None:                                   # POD.jl:111-118
+            errorhandle(snaps, nmodes, 0.0, nmodes, nmodes)
+            self.min_renergy, self.min_nmodes, self.max_nmodes = 0.0, nmodes, nmodes
+            self.nmodes = nmodes
+        else:                                                    # POD.jl:91-110
+            if max_nmodes is None:
+                max_nmodes = len(snaps[0]) if is_vov(snaps) else 1   # length(snaps[1])
+            nm = min_nmodes
+            errorhandle(snaps, nm, min_renergy, min_nmodes, max_nmodes)
+            self.min_renergy, self.min_nmodes, self.max_nmodes = min_renergy, min_nmodes, max_nmodes
+            self.nmodes = nm
+        self.snapshots = snaps
+        self.rbasis: Optional[Array] = None      # `missing` before reduce!
+        self.renergy = 1.0                       # one(T)
+        self.spectrum: Optional[Array] = None
+
+
+def determine_truncation(s: Array, min_nmodes: int, max_nmodes: int,
+                         min_renergy: float) -> Tuple[int, float]:
+    """POD.jl:121-132, quirks included: energy is in plain sigma (not sigma^2); the loop
+    adds ``s[nmodes + 1]`` (1-based) i.e. the sigma AFTER the newly counted one; running
+    past the end raises (Julia: BoundsError; here IndexError)."""
+    nmodes = min_nmodes
+    overall_energy = float(np.sum(s))
+    energy = float(np.sum(s[:nmodes])) / overall_energy
+    while energy < min_renergy and nmodes < max_nmodes:
+        nmodes += 1
+        if nmodes + 1 > len(s):                       # s[nmodes + 1], 1-based
+            raise IndexError("BoundsError: determine_truncation ran past the spectrum")
+        energy += float(s[nmodes]) / overall_energy   # 0-based s[nmodes] == 1-based s[nmodes+1]
+    return nmodes, energy
+
+
+# --------------------------------------------------------------------------------------
+# third-party seams -- POD.jl:8-27
+# --------------------------------------------------------------------------------------
+def _as_matrix(snaps: Snapshots) -> Array:
+    return matricize(snaps) if is_vov(snaps) else np.asarray(snaps, dtype=np.float64)
+
+
+def _svd(snaps: Snapshots) -> Tuple[Array, Array, Array]:
+    """POD.jl:8-13 -> LinearAlgebra.svd(X): thin SVD by LAPACK dgesdd on a copy.
+    Returns (U m x r, s r, V n x r), r = min(m, n), s descending."""
+    X = _as_matrix(snaps)
+    u, s, vt = sla.svd(X, full_matrices=False, lapack_driver="gesdd")
+    return u, s, vt.T
+
+
+def _tsvd(snaps: Snapshots, k: int = 1) -> Tuple[Array, Array, Array]:
+    """POD.jl:15-20 -> TSVD.tsvd(X, k).  TSVD.jl (compat "0.4.4", not vendored) is a
+    Golub-Kahan-Lanczos solver with a random start vector and tolconv ~ 1.5e-8, so it
+    cannot itself be a 1e-10 oracle; the oracle is the exact top-k triplets it converges
+    to, taken from dgesdd."""
+    u, s, v = _svd(snaps)
+    return u[:, :k], s[:k], v[:, :k]
+
+
+def _rsvd(snaps: Snapshots, k: int, p: int, omega: Array) -> Tuple[Array, Array, Array]:
+    """POD.jl:22-27 -> RandomizedLinAlg.rsvd(X, k, p) (compat "0.1", not vendored;
+    Halko-Martinsson-Tropp Alg. 4.1 + 5.1, no power iterations): Y = X*Omega with Omega
+    n x (k+p); Q = thin-QR(Y).Q, truncated to its first k columns when p > 0; B = Q'X;
+    svd(B); U = (Q*U_B)[:, 1:k].  The reference draws Omega from Julia's unseeded global
+    RNG; north_star fixes that by sharing a seeded Omega between oracle and library, so
+    Omega is an explicit argument here."""
+    X = _as_matrix(snaps)
+    n = X.shape[1]
+    assert omega.shape == (n, k + p)
+    Y = X @ omega
+    Q, _ = sla.qr(Y, mode="economic")
+    if p > 0:
+        Q = Q[:, :k]
+    B = Q.T @ X
+    ub, s, vt = sla.svd(B, full_matrices=False, lapack_driver="gesdd")
+    U = (Q @ ub)[:, :k]
+    return U, s[:k], vt[:k, :].T
+
+
+# --------------------------------------------------------------------------------------
+# reduce! -- POD.jl:156-166, 195-202, 231-238
+# --------------------------------------------------------------------------------------
+def reduce(pod: POD, alg, omega: Optional[Array] = None) -> None:
+    """``reduce!(pod, alg)``: mutates ``pod`` and returns None (POD.jl:156,195,231)."""
+    if isinstance(alg, SVD):                                    # POD.jl:156-166
+        u, s, _v = _svd(pod.snapshots)
+        pod.nmodes, pod.renergy = determine_truncation(
+            s, pod.min_nmodes, pod.max_nmodes, pod.min_renergy)
+        pod.rbasis = np.array(u[:, :pod.nmodes], order="F")
+        pod.spectrum = np.array(s)                              # FULL spectrum
+    elif isinstance(alg, TSVD):                                 # POD.jl:195-202
+        u, s, v = _tsvd(pod.snapshots, pod.nmodes)
+        n_max = min(u.shape[0], v.shape[0])
+        pod.renergy = float(np.sum(s) / (np.sum(s) + (n_max - pod.nmodes) * s[-1]))
+        pod.rbasis = np.array(u, order="F")
+        pod.spectrum = np.array(s)
+    elif isinstance(alg, RSVD):                                 # POD.jl:231-238
+        if omega is None:
+            raise ValueError("oracle RSVD needs the shared Omega")
+        u, s, v = _rsvd(pod.snapshots, pod.nmodes, alg.p, omega)
+        n_max = min(u.shape[0], v.shape[0])
+        pod.renergy = float(np.sum(s) / (np.sum(s) + (n_max - pod.nmodes) * s[-1]))
+        pod.rbasis = np.array(u, order="F")
+        pod.spectrum = np.array(s)
+    else:
+        raise TypeError(alg)
+    return None
+
+
+# --------------------------------------------------------------------------------------
+# DEIM -- src/deim.jl:9-28
+# --------------------------------------------------------------------------------------
+def argmax_first(r: Array) -> int:
+    """Julia ``argmax`` (deim.jl:14,24): first maximal element, NaN counts as maximal.
+    Returns a 0-based position."""
+    nan = np.isnan(r)
+    if nan.any():
+        return int(np.flatnonzero(nan)[0])
+    return int(np.argmax(r))        # numpy returns the first occurrence of the maximum
+
+
+def _backslash(A: Array, b: Array) -> Array:
+    """Julia's generic square ``A \\ b`` (LinearAlgebra/src/generic.jl ``\\``): diagonal
+    -> divide (this is the 1x1 case of deim.jl:21 at l=2); lower/upper triangular ->
+    substitution; otherwise ``lu(A) \\ b`` = dgetrf + dgetrs with partial pivoting.
+    A zero pivot raises, like Julia's SingularException."""
+    n = A.shape[0]
+    lower = not np.any(np.triu(A, 1))
+    upper = not np.any(np.tril(A, -1))
+    if lower and upper:
+        d = np.diag(A)
+        if np.any(d == 0):
+            raise np.linalg.LinAlgError("SingularException")
+        return b / d
+    if lower or upper:
+        if np.any(np.diag(A) == 0):
+            raise np.linalg.LinAlgError("SingularException")
+        return sla.solve_triangular(A, b, lower=lower, check_finite=False)
+    lu, piv = sla.lu_factor(A, check_finite=False)
+    if np.any(np.diag(lu) == 0):
+        raise np.linalg.LinAlgError("SingularException")
+    return sla.lu_solve((lu, piv), b, check_finite=False)
+
+
+def deim_interpolation_indices(basis: Array) -> Array:
+    """deim.jl:9-28, line for line.  ``basis`` is m x k dense; returns k 1-based Int64
+    indices.  l.13-14: first index = argmax |column 1|.  For l = 2..k: gather the
+    selected rows (l.16-20), solve (P'U) c = P'u_l with the generic backslash (l.21),
+    r = U*c by dgemv (l.22), r = |u_l - r| (l.23), next index = argmax r (l.24)."""
+    basis = np.asarray(basis, dtype=np.float64)
+    m, dim = basis.shape
+    indices = np.zeros(dim, dtype=np.int64)
+    r = np.abs(basis[:, 0])
+    indices[0] = argmax_first(r)
+    for l in range(1, dim):
+        U = basis[:, :l]
+        P = indices[:l]
+        PtU = U[P, :]
+        ul = basis[:, l]
+        Ptul = ul[P]
+        c = _backslash(PtU, Ptul)
+        r = U @ c
+        r = np.abs(ul - r)
+        indices[l] = argmax_first(r)
+    return indices + 1
+
+
+# --------------------------------------------------------------------------------------
+# Row-sharded restatements (the exchange steps of SURVEY.md section 8e), used to check
+# that the multi-GPU algorithm -- not just its kernels -- reproduces the reference.
+# ``allgather(obj) -> list`` is supplied by the caller (torch.distributed gloo in tests).
+# --------------------------------------------------------------------------------------
+def _better(val_a: float, idx_a: int, val_b: float, idx_b: int) -> bool:
+    """True when candidate a beats b: NaN is maximal, then larger value, then the lower
+    global index (Julia's first-index tie-break carried across shard boundaries)."""
+    na, nb = math.isnan(val_a), math.isnan(val_b)
+    if na or nb:
+        if na and nb:
+            return idx_a < idx_b
+        return na
+    if val_a != val_b:
+        return val_a > val_b
+    return idx_a < idx_b
+
+
+def deim_interpolation_indices_sharded(local_basis: Array, row_offset: int, allgather) -> Array:
+    """DEIM over contiguous row shards: each rank proposes (value, global index, row of
+    the basis at that index); every rank picks the same winner and appends its row to
+    the replicated P'U.  Same arithmetic per row as deim.jl:21-24."""
+    local_basis = np.asarray(local_basis, dtype=np.float64)
+    _, dim = local_basis.shape
+    indices = np.zeros(dim, dtype=np.int64)
+    W = np.zeros((dim, dim))                       # W[i, :] = basis[p_i, :]
+    for l in range(dim):
+        ul = local_basis[:, l]
+        if l == 0:
+            r = np.abs(ul)
+        else:
+            c = _backslash(W[:l, :l], W[:l, l])
+            r = np.abs(ul - local_basis[:, :l] @ c)
+        if r.size:
+            j = argmax_first(r)
+            cand = (float(r[j]), row_offset + j, local_basis[j, :].copy())
+        else:
+            cand = (-1.0, -1, np.zeros(dim))       # empty shard never wins
+        best = None
+        for val, gi, row in allgather(cand):
+            if gi < 0:
+                continue
+            if best is None or _better(val, gi, best[0], best[1]):
+                best = (val, gi, row)
+        indices[l] = best[1]
+        W[l, :] = best[2]
+    return indices + 1
+
+
+def pod_svd_sharded(local_X: Array, allreduce_sum) -> Tuple[Array, Array]:
+    """Row-sharded POD factorisation as the library performs it (CholeskyQR2 + SVD of the
+    small factor): partial Gram matrices are summed across shards, everything n x n is
+    replicated.  Returns (s, V).  Used to validate the exchange pattern on CPU."""
+    X = np.array(local_X, dtype=np.float64, order="F")
+    G = allreduce_sum(X.T @ X)
+    R1 = sla.cholesky(G, lower=False)
+    X1 = sla.solve_triangular(R1, X.T, trans="T", lower=False).T
+    G2 = allreduce_sum(X1.T @ X1)
+    R2 = sla.cholesky(G2, lower=False)
+    R = R2 @ R1
+    _, s, vt = sla.svd(R, lapack_driver="gesdd")
+    return s, vt.T
+
+
+# --------------------------------------------------------------------------------------
+# parity metrics used by tests and bench
+# --------------------------------------------------------------------------------------
+def sigma_error(s_ref: Array, s: Array, floor: float = 1e-5) -> float:
+    """SURVEY.md section 8d gate: relative error for sigma_i >= floor*sigma_1, absolute
+    error / sigma_1 below the floor.  Returns the max over i."""
+    s_ref = np.asarray(s_ref, dtype=np.float64)
+    s = np.asarray(s, dtype=np.float64)
+    big = s_ref >= floor * s_ref[0]
+    err = np.where(big, np.abs(s - s_ref) / np.where(big, s_ref, 1.0),
+                   np.abs(s - s_ref) / s_ref[0])
+    return float(err.max())
+
+
+def subspace_sine(U_ref: Array, U: Array) -> float:
+    """Sine of the largest principal angle between span(U_ref) and span(U) (both with
+    orthonormal columns up to rounding)."""
+    Qr, _ = np.linalg.qr(U_ref)
+    Q, _ = np.linalg.qr(U)
+    resid = Q - Qr @ (Qr.T @ Q)
+    return float(np.linalg.norm(resid, 2))

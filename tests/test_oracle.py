@@ -1,0 +1,154 @@
+"""Pins the oracle: analytic answers of the reference's fixtures, the reference's own
+range assertions, and the committed golden vectors (CPU only)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import mor_oracle as O
+from conftest import sin_fixture
+
+
+def test_f1_interface_fixture_analytic():
+    # test/interface.jl:3-17 -- analytic: s=[3,1], rbasis=+-[1,0], renergy .75 (SVD) / .5 (TSVD,RSVD)
+    X = np.array([[3.0, 0.0], [0.0, 1.0]], order="F")
+    vov = [np.array([3.0, 0.0]), np.array([0.0, 1.0])]
+    for snaps in (X, vov):
+        for alg, re in ((O.SVD(), 0.75), (O.TSVD(), 0.5), (O.RSVD(), 0.5)):
+            pod = O.POD(snaps, 1)
+            assert O.reduce(pod, alg, omega=np.array([[1.0], [0.25]])) is None
+            assert pod.rbasis.shape == (2, 1)
+            assert len(pod.spectrum) >= pod.nmodes
+            assert pod.nmodes == 1
+            assert 0.0 < pod.renergy <= 1.0
+            assert pod.renergy == pytest.approx(re, abs=1e-14)
+            if isinstance(alg, O.RSVD):     # rank-1 sketch of a rank-2 matrix: approximate
+                assert 1.0 <= pod.spectrum[0] <= 3.0 + 1e-14
+            else:
+                assert pod.spectrum[0] == pytest.approx(3.0, abs=1e-14)
+                np.testing.assert_allclose(np.abs(pod.rbasis[:, 0]), [1.0, 0.0], atol=1e-14)
+
+
+def test_f2_sin_fixture_golden(golden):
+    S = sin_fixture()
+    pod = O.POD(S, 3)
+    O.reduce(pod, O.SVD())
+    np.testing.assert_allclose(pod.spectrum, golden["F2"]["spectrum"], rtol=1e-12, atol=1e-15)
+    assert pod.renergy == pytest.approx(golden["F2"]["renergy_svd_k3"], rel=1e-13)
+    pod = O.POD(S, 3)
+    O.reduce(pod, O.TSVD())
+    assert pod.renergy == pytest.approx(golden["F2"]["renergy_tsvd_k3"], rel=1e-13)
+    assert pod.spectrum.shape == (3,)
+    Q, _ = sla.qr(S, mode="economic")
+    assert O.deim_interpolation_indices(Q[:, :5]).tolist() == golden["F2"]["deim_Q5"] == [20, 11, 16, 5, 19]
+    U, _, _ = O._svd(S)
+    assert O.deim_interpolation_indices(U).tolist() == golden["F2"]["deim_U10"]
+
+
+def test_f5_truncation_quirks(golden):
+    s = np.array([4.0, 3.0, 2.0, 1.0])
+    # probe from SURVEY 8a: mre=0.5 -> (2, 0.6) although the true 2-mode energy is 0.7
+    assert O.determine_truncation(s, 1, 4, 0.5) == (2, pytest.approx(0.6))
+    for case in golden["F5"]:
+        n, e = O.determine_truncation(s, *case["args"])
+        assert n == case["out"][0] and e == pytest.approx(case["out"][1], rel=1e-15)
+    with pytest.raises(IndexError):      # Julia: BoundsError
+        O.determine_truncation(s, 1, 4, 1.0)
+
+
+def test_pod_ctor_defaults_and_asserts():
+    X = np.ones((5, 3))
+    assert O.POD(X).max_nmodes == 1                       # length(snaps[1]) of a Matrix
+    assert O.POD([np.ones(5)] * 3).max_nmodes == 5        # ... of a Vector{Vector}
+    with pytest.raises(AssertionError):
+        O.POD(np.ones((1, 3)), 1)
+    with pytest.raises(AssertionError):
+        O.POD(X, 4)
+    with pytest.raises(AssertionError):
+        O.POD(X, 0)
+    with pytest.raises(AssertionError):
+        O.POD(X, min_renergy=1.5)
+    with pytest.raises(AssertionError):
+        O.POD(X, min_nmodes=2, max_nmodes=1)
+
+
+def test_lorenz_ranges():
+    # test/DataReduction.jl:27-67 (range assertions only; trajectory via scipy instead of Tsit5)
+    from scipy.integrate import solve_ivp
+
+    def lorenz(t, u):
+        return [10.0 * (u[1] - u[0]), u[0] * (28.0 - u[2]) - u[1], u[0] * u[1] - (8 / 3) * u[2]]
+    sol = solve_ivp(lorenz, (0, 100), [1.0, 0.0, 0.0], rtol=1e-8, atol=1e-8, max_step=0.05)
+    X = np.asfortranarray(sol.y)
+    vov = [X[:, j].copy() for j in range(X.shape[1])]
+    assert O.matricize(vov).shape == X.shape
+    p1, p2 = O.POD(X, 2), O.POD(vov, 2)
+    O.reduce(p1, O.SVD()); O.reduce(p2, O.SVD())
+    np.testing.assert_allclose(p1.rbasis, p2.rbasis)
+    assert p1.renergy == pytest.approx(p2.renergy)
+    assert p1.rbasis.shape == (3, 2) and p1.renergy > 0.9
+    pe = O.POD(X, min_renergy=0.1, min_nmodes=1, max_nmodes=2)
+    O.reduce(pe, O.SVD())
+    assert pe.nmodes == 1 and pe.renergy > 0.1
+    pt = O.POD(X, 2)
+    O.reduce(pt, O.TSVD())
+    assert pt.rbasis.shape == (3, 2) and pt.renergy > 0.7
+
+
+def test_deim_golden_random(golden):
+    for case in golden["deim_random"]:
+        rng = np.random.Generator(np.random.PCG64(case["seed"]))
+        Q, _ = np.linalg.qr(rng.standard_normal((case["m"], case["k"])))
+        assert O.deim_interpolation_indices(Q).tolist() == case["indices"]
+
+
+def test_deim_ties_and_nan():
+    # exact ties: duplicated rows with exactly representable entries -> first index wins
+    B = np.zeros((8, 2))
+    B[:, 0] = [1, -2, 2, 0.5, 2, -2, 1, 0]      # |.| max = 2 first at row 2 (1-based)
+    B[:, 1] = [0, 1, 1, 4, -3, 4, 4, 4]
+    idx = O.deim_interpolation_indices(B)
+    assert idx[0] == 2
+    # second step: c = B[1,1]/B[1,0] = -0.5 ; r = |u2 + 0.5 u1| -> [.5,0,2,4.25,2,3,4.5,4] -> row 7
+    assert idx[1] == 7
+    Bn = B.copy(); Bn[5, 0] = np.nan; Bn[6, 0] = np.nan
+    assert O.deim_interpolation_indices(Bn)[0] == 6      # first NaN is maximal
+    # l=2 uses the 1x1 divide branch of the generic backslash; singular -> exception
+    Z = np.zeros((4, 2)); Z[:, 1] = 1
+    with pytest.raises(np.linalg.LinAlgError):
+        O.deim_interpolation_indices(Z)
+
+
+def test_sharded_restatements_match_unsharded():
+    rng = np.random.Generator(np.random.PCG64(7))
+    Q, _ = np.linalg.qr(rng.standard_normal((301, 12)))
+    Q[150] = Q[17]                                   # exact tie across a shard boundary
+    full = O.deim_interpolation_indices(Q)
+    bounds = [0, 100, 100, 250, 301]                 # includes an empty shard
+    shards = [(Q[a:b], a) for a, b in zip(bounds[:-1], bounds[1:])]
+    # lock-step emulation of the all-gather: run the ranks as coroutines over shared state
+    import threading
+    n = len(shards)
+    barrier = threading.Barrier(n)
+    slots = [None] * n
+    out = [None] * n
+
+    def run(r):
+        def allgather(x):
+            slots[r] = x
+            barrier.wait()
+            res = list(slots)
+            barrier.wait()
+            return res
+        out[r] = O.deim_interpolation_indices_sharded(shards[r][0], shards[r][1], allgather)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(n)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    for r in range(n):
+        assert out[r].tolist() == full.tolist()
+
+
+def test_parity_metrics():
+    s = np.array([1.0, 1e-3, 1e-9])
+    assert O.sigma_error(s, s * (1 + 1e-12)) < 2e-12
+    assert O.sigma_error(s, s + np.array([0, 0, 1e-12])) == pytest.approx(1e-12)
+    Q, _ = np.linalg.qr(np.random.default_rng(0).standard_normal((50, 4)))
+    assert O.subspace_sine(Q, -Q[:, ::-1]) < 1e-14
