@@ -51,8 +51,33 @@ void DevBuf::release() {
     bytes = 0;
 }
 
+int32_t scratch(size_t bytes, void** out) {
+    Ctx& c = g_ctx;
+    if (bytes > c.scratch_bytes) {
+        if (c.scratch_p) {
+            cudaStreamSynchronize(c.stream);
+            cudaFree(c.scratch_p);
+            c.scratch_p = nullptr;
+            c.scratch_bytes = 0;
+        }
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&c.scratch_p, want);
+        if (e != cudaSuccess) {
+            c.scratch_p = nullptr;
+            return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+        }
+        c.scratch_bytes = want;
+    }
+    *out = c.scratch_p;
+    return MOR_OK;
+}
+
 Timer::Timer(int slot_) : slot(slot_) {}
 Timer::~Timer() {
+    if (running) {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
     for (auto& s : spans) {
         cudaEventDestroy(s.first);
         cudaEventDestroy(s.second);
@@ -125,6 +150,9 @@ int32_t mor_b200_shutdown(void) {
     if (g_ctx.ready) {
         cudaSetDevice(g_ctx.device);
         cudaStreamSynchronize(g_ctx.stream);
+        if (g_ctx.scratch_p) cudaFree(g_ctx.scratch_p);
+        g_ctx.scratch_p = nullptr;
+        g_ctx.scratch_bytes = 0;
         if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
         g_ctx.own_stream = nullptr;
         g_ctx.stream = nullptr;

@@ -43,10 +43,15 @@ struct Ctx {
     int rank = 0, nranks = 1;
     double timings[MOR_T_NSLOTS] = {0};
     int64_t launches = 0;
+    void* scratch_p = nullptr;          // grow-only workspace (partial tiles, packed W)
+    size_t scratch_bytes = 0;
 };
 Ctx& ctx();
 int32_t require_ctx();
 inline void count_launch(int n = 1) { ctx().launches += n; }
+// Grow-only device workspace of at least `bytes`; contents are only valid until the next
+// scratch() call on this context (all users are ordered on ctx().stream).
+int32_t scratch(size_t bytes, void** out);
 
 // RAII device buffer (freed with cudaFree on destruction)
 struct DevBuf {
@@ -109,20 +114,34 @@ int32_t gemm_nn(const double* X, int64_t ldx, int n, const double* W, int ldw, i
                 double* Y, int64_t ldy, int upper);
 
 // ---- small dense kernels (small.cu) and Jacobi SVD (jacobi.cu) -------------------------------
-struct CholInfo {
-    double delta_f;   // ||G_s - I||_F of the scaled Gram matrix
-    double shift;     // shift finally used (0 if none)
-    int ok;
+struct SmallInfo {
+    double delta2;   // ||D^-1 G D^-1 - I||_F^2
+    int nonfinite;   // Inf/NaN seen in G
+    int nzero;       // all-zero columns (G_jj == 0)
+    int chol_fail;   // 1-based index of the first non-positive pivot, 0 = ok
+    int rotations;   // Jacobi rotations applied in the last sweep
 };
-int32_t small_scale_chol(double* G, int n, int ld, double* D, double* Rs, CholInfo* info);
-int32_t small_trinv_upper(const double* R, int n, int ld, double* Rinv);
+int32_t small_info_reset(SmallInfo* d_info);
+int32_t small_info_read(const SmallInfo* d_info, SmallInfo* h);
+int32_t small_diag(const double* G, int n, int ld, double* D, SmallInfo* d_info);
+int32_t small_scale(const double* G, int n, int ld, const double* D, double shift, double* Gs, int lds,
+                    SmallInfo* d_info);
+int32_t small_chol_upper(double* A, int n, int ld, SmallInfo* d_info);   // A = R'R, lower part zeroed
+int32_t small_trinv_upper(const double* R, int n, int ld, double* Rinv, int ldi);
 int32_t small_gemm(bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda,
                    const double* B, int ldb, double beta, double* C, int ldc);
-// One-sided Jacobi on the columns of A (rows x n, ld).  On return the columns are
-// orthogonal, sorted by decreasing norm; sigma[j] = ||A(:,j)||.  If J != nullptr it
-// receives the accumulated rotations (n x n, ld = ldj), A_in * J = A_out.
-int32_t jacobi_svd(double* A, int rows, int n, int ld, double* J, int ldj, double* sigma,
-                   int* sweeps_out);
+// A[i][j] *= s with s = d[i] (rows) or d[j]; inv: s = 1/d; a zero entry of d acts as 1
+int32_t small_scale_rc(double* A, int m, int n, int ld, const double* d, bool rows, bool inv);
+int32_t small_identity(double* A, int n, int ld);
+int32_t small_zero_rows(double* A, int m, int n, int ld, const double* flag);
+int32_t transpose(const double* in, int64_t rows, int64_t cols, int64_t ldin, double* out, int64_t ldout);
+int32_t gather_cols(const double* in, int ldin, int rows, int ncols, const int* d_perm, const double* d_scale,
+                    double* out, int ldout);
+// One-sided Jacobi on the columns of A (rows x n, lda), in place: on return the columns are
+// mutually orthogonal (A_in * V = A_out, V n x n accumulated if non-null).  sigma = column
+// norms sorted descending, order[j] = column holding the j-th largest.
+int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std::vector<double>& sigma,
+                   std::vector<int>& order, int* sweeps_out);
 
 // ---- POD driver (pod.cu) ---------------------------------------------------------------------
 }  // namespace mor
