@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of libmor_b200 (BASELINE.json):
+
+  POD `reduce!(pod, SVD())` of the synthetic 16,777,216 x 1024 FP64 snapshot matrix (k = 64),
+  rows sharded over the N ranks (strong scaling), reported as algorithmic FP64 TFLOP/s
+  (2mn^2 + 2mnk flop) and ms; plus DEIM `deim_interpolation_indices` on a
+  16,777,216 x 256 orthonormal basis as ms and algorithmic HBM GB/s (4mk(k+1) bytes).
+
+One "step" = one full pass of the hot path over the resident input: factorisation
+(Gram -> Cholesky -> Jacobi) + basis U_k.  `value` is device-resident (inputs in HBM when the
+timed region starts); `e2e` goes through the host-pointer C ABI (mor_b200_pod_factor +
+mor_b200_pod_basis: what the Julia shim calls) with pinned host buffers, copies inside the
+timed region.  `--impl reference` times the CPU restatement of the reference path (scipy
+OpenBLAS dgesdd = what LinearAlgebra.svd dispatches to) on a bounded row sample.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "modelorderreduction.jl_b200", "python"))
+
+M_FULL, N_COLS, K_MODES = 16 * 2**20, 1024, 64
+DEIM_M, DEIM_K = 16 * 2**20, 256
+METRIC = "POD SVD() FP64 TFLOP/s at 16Mx1024 (algorithmic 2mn^2+2mnk flop / time); DEIM k=256 ms and HBM GB/s alongside"
+
+
+def pod_flops(m, n, k):
+    return 2.0 * m * n * n + 2.0 * m * n * k
+
+
+def deim_bytes(m, k):
+    return 4.0 * m * k * (k + 1)
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING a timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference path on the box's host cores
+# ------------------------------------------------------------------------------------------
+def cpu_pod_sample(rows, steps, warmup):
+    """Times oracle reduce!(POD(X, k), SVD()) (dgesdd through scipy-OpenBLAS, all host threads)
+    on a `rows` x 1024 slice of the workload.  Returns (TFLOP/s algorithmic, ms/step, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import mor_oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(3)
+    X = np.asfortranarray(rng.standard_normal((rows, N_COLS)) * np.logspace(0, -3, N_COLS))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        pod = O.POD(X, K_MODES)
+        O.reduce(pod, O.SVD())
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return pod_flops(rows, N_COLS, K_MODES) / t * 1e-12, t * 1e3, threads
+
+
+def cpu_deim_sample(rows, k):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import mor_oracle as O
+    rng = np.random.default_rng(5)
+    Q, _ = np.linalg.qr(rng.standard_normal((rows, k)))
+    t0 = time.perf_counter()
+    O.deim_interpolation_indices(Q)
+    t = time.perf_counter() - t0
+    return deim_bytes(rows, k) / t * 1e-9, t * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    tf, ms, threads = cpu_pod_sample(rows, args.steps, args.warmup)
+    sample = (f"oracle reduce!(POD(X,{K_MODES}),SVD()) = scipy/OpenBLAS dgesdd on a {rows}x{N_COLS} row sample of "
+              f"the workload, {threads} BLAS threads; every stage is O(m), so TFLOP/s carries over to 16M rows")
+    line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample,
+                             "extrapolated_full_ms": pod_flops(M_FULL, N_COLS, K_MODES) / (tf * 1e12) * 1e3},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    m = args.rows
+    cfg = {"workload": f"POD reduce!(pod, SVD()) of a synthetic {m}x{N_COLS} FP64 snapshot matrix (N(0,1) entries, "
+                       f"column scale 10^(-3j/(n-1)), Philox seed 3), nmodes={K_MODES}; "
+                       f"DEIM on a {args.deim_rows}x{DEIM_K} orthonormal basis",
+           "m": m, "n": N_COLS, "k": K_MODES, "parallelism": f"rows/{world}",
+           "l2": "inputs (>= 17 GB per GPU) are larger than the 126 MB L2; no flush needed"}
+    if m != M_FULL:
+        cfg["note"] = "NOT the named 16M-row workload (--rows override)"
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mor_b200 import _lib
+    from mor_b200 import dist as mdist
+    from mor_b200.device import DeviceMatrix, deim_indices_dev, orthonormalize_dev, pod_factor_dev
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libmor_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mdist.init_from_torch(local)
+    else:
+        mdist.init(local)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream()
+    _lib.check(lib.mor_b200_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- live roofline denominators (FP64 DMMA issue rate, streaming read) ----------------------
+    lib.mor_dbg_peaks.restype = C.c_int32
+    pk_t, pk_g = C.c_double(0), C.c_double(0)
+    _lib.check(lib.mor_dbg_peaks(3, 4, C.byref(pk_t), C.byref(pk_g)))
+    peaks_file = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks_file = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = float(peaks_file.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks_file else "6650 GB/s (of fallback)"
+
+    M, n, k = args.rows, N_COLS, K_MODES
+    row0, m_loc = mdist.shard_rows(M, world, rank)
+    X = DeviceMatrix.alloc(m_loc, n).synth(_lib.SYNTH_GRADED, seed=3, global_row0=row0, param=3.0)
+    U = DeviceMatrix.alloc(m_loc, k)
+    slots = ("total", "gram", "core", "basis", "comm", "apply")
+    acc = {s: 0.0 for s in slots}
+    info = {}
+
+    def step(collect=False):
+        f = pod_factor_dev(X, _lib.MOR_SVD, k, m_global=M)
+        if collect:
+            t = _lib.last_timings()
+            for s in slots:
+                acc[s] += t[s] if s != "total" else 0.0
+        f.basis(k, U)
+        if collect:
+            t = _lib.last_timings()
+            acc["basis"] += t["basis"]
+            info["passes"], info["sweeps"] = f.info()
+            info["s"] = f.s
+        f.free()
+
+    for _ in range(args.warmup):
+        step()
+    lib.mor_b200_launch_count(1)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(collect=True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    pod_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = int(lib.mor_b200_launch_count(0))
+    gram_ms = max_over_ranks(acc["gram"] / args.steps)
+    parts = {s: acc[s] / args.steps for s in slots if s != "total"}
+    value = pod_flops(M, n, k) / (pod_ms * 1e-3) * 1e-12
+
+    # ---- validity checks outside the timed region ---------------------------------------------
+    lib.mor_dbg_gemm_tn.restype = C.c_int32
+    UtU = DeviceMatrix.alloc(k, k)
+    _lib.check(lib.mor_dbg_gemm_tn(U.handle, U.handle, UtU.handle))
+    g = torch.from_numpy(UtU.to_host()).cuda()
+    if world > 1:
+        dist.all_reduce(g)
+    orth_err = float((g - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item())
+    s = info["s"]
+    d = 10.0 ** (-3.0 * np.arange(n) / (n - 1))
+    sig_dev = float(np.max(np.abs(s / (math.sqrt(M) * d) - 1.0)))   # sigma_j ~ sqrt(m) d_j up to O(sqrt(n/m))
+    checks = {"basis_orthonormality_max_abs": orth_err, "sigma_vs_sqrt_m_times_scale_max_rel": sig_dev,
+              "cholqr_passes": info["passes"], "jacobi_sweeps": info["sweeps"]}
+    UtU.free()
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        need_gb = (m_loc * n + m_loc * k) * 8 / 1e9
+        avail = mem_available_gb() / max(1, min(world, 8))
+        if need_gb * 1.15 + 8 > avail:
+            e2e = {"value": None, "unit": "TFLOP/s", "skipped": f"host shard needs {need_gb:.0f} GB pinned, "
+                   f"{avail:.0f} GB available per rank"}
+        else:
+            Xh, Uh = C.c_void_p(), C.c_void_p()     # pinned, column-major m_loc x n and m_loc x k
+            _lib.check(lib.mor_b200_host_alloc(m_loc * n * 8, C.byref(Xh)))
+            _lib.check(lib.mor_b200_host_alloc(m_loc * k * 8, C.byref(Uh)))
+            _lib.check(lib.mor_b200_mat_download(X.handle, Xh, max(m_loc, 1)))
+            X.free(); U.free()
+            S = np.empty(n); nS = C.c_int64(0)
+
+            def e2e_step():
+                h = C.c_void_p()
+                _lib.check(lib.mor_b200_pod_factor(Xh, m_loc, n, max(m_loc, 1), _lib.MOR_SVD,
+                                                   k, 0, None, 0, C.byref(h), S.ctypes.data, C.byref(nS)))
+                _lib.check(lib.mor_b200_pod_basis(h, k, Uh, max(m_loc, 1), None, 0))
+                lib.mor_b200_pod_free(h)
+
+            for _ in range(args.e2e_warmup):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            barrier()
+            e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps * 1e3)
+            e2e = {"value": pod_flops(M, n, k) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(sum_over_ranks(m_loc * n * 8)),
+                   "d2h_bytes_per_step": int(sum_over_ranks(m_loc * k * 8) + n * 8),
+                   "steps": args.e2e_steps, "warmup": args.e2e_warmup, "host_memory": "pinned",
+                   "api": "mor_b200_pod_factor + mor_b200_pod_basis (host pointers)"}
+            lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
+    X.free(); U.free()
+
+    # ---- DEIM: 16M x 256 orthonormal basis, row-sharded ------------------------------------------
+    Md, kd = args.deim_rows, DEIM_K
+    r0d, md_loc = mdist.shard_rows(Md, world, rank)
+    B = DeviceMatrix.alloc(md_loc, kd).synth(_lib.SYNTH_GAUSS, seed=5, global_row0=r0d, param=1.0 / math.sqrt(Md))
+    orth_passes = orthonormalize_dev(B)
+    dacc = {"deim_step": 0.0, "deim_tail": 0.0, "comm": 0.0}
+    for _ in range(args.warmup):
+        idx = deim_indices_dev(B)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        idx = deim_indices_dev(B)
+        t = _lib.last_timings()
+        for s_ in dacc:
+            dacc[s_] += t[s_]
+    e1.record(stream)
+    barrier()
+    deim_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    deim_step_ms = max_over_ranks(dacc["deim_step"] / args.steps)
+    deim_gbs = deim_bytes(Md, kd) / (deim_ms * 1e-3) * 1e-9
+    deim = {"ms": deim_ms, "algorithmic_gbs": deim_gbs, "m": Md, "k": kd, "distinct_indices": len(set(idx.tolist())),
+            "basis": f"Philox Gaussian orthonormalised by the library's CholeskyQR ({orth_passes} passes)",
+            "roofline": {"bound": "hbm", "kernel": "deim_step_kernel (all k launches)",
+                         "achieved": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9,
+                         "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                         "frac": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9 / hbm_peak,
+                         "live_read_peak_gbs": pk_g.value, "traffic": None},
+            "tail_ms": dacc["deim_tail"] / args.steps}
+    B.free()
+
+    if rank != 0:
+        return
+    # ---- CPU baseline: the oracle on this box's host cores (N = 1 only, bounded sample) ---------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        tf, ms, threads = cpu_pod_sample(args.cpu_rows, 2, 1)
+        dg, dms = cpu_deim_sample(args.cpu_deim_rows, DEIM_K)
+        cpu = {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+               "sample": f"oracle (scipy/OpenBLAS dgesdd, {threads} threads) on {args.cpu_rows}x{n} rows of the "
+                         f"workload: {ms:.0f} ms/step; extrapolated to {M} rows: "
+                         f"{pod_flops(M, n, k) / (tf * 1e12):.0f} s",
+               "deim": {"algorithmic_gbs": dg, "ms": dms,
+                        "sample": f"oracle deim_interpolation_indices (dgetrf/dgemv) on {args.cpu_deim_rows}x{DEIM_K}"}}
+    gram_flops = m_loc * n * (n + 1.0)      # minimal flops of a symmetric Gram matrix, per rank
+    achieved = gram_flops / (gram_ms * 1e-3) * 1e-12
+    line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": pod_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<128,128,...> (symmetric Gram, DMMA.8x8x4)",
+                         "achieved": achieved, "peak": pk_t.value, "unit": "TFLOP/s",
+                         "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark in this run (MEASURED_PEAKS.json "
+                                        "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
+                         "frac": achieved / pk_t.value if pk_t.value else None, "traffic": None,
+                         "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
+            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=M_FULL, help="override the 16M-row workload (testing only)")
+    ap.add_argument("--deim-rows", type=int, default=DEIM_M)
+    ap.add_argument("--cpu-rows", type=int, default=65536)
+    ap.add_argument("--cpu-deim-rows", type=int, default=262144)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-warmup", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,10 @@ const char* mor_b200_last_error(void);
 /* Run on the caller's CUDA stream (cudaStream_t as void*); NULL restores the own stream. */
 int32_t mor_b200_set_stream(void* cuda_stream);
 int32_t mor_b200_sync(void);
+/* Page-locked host staging memory (cudaHostAlloc): snapshots handed to the host-pointer entry
+ * points from such a buffer move at full PCIe speed.  Optional -- any host pointer works. */
+int32_t mor_b200_host_alloc(uint64_t bytes, void** out);
+int32_t mor_b200_host_free(void* p);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------------------- */
 /* Rank 0 creates a 128-byte NCCL unique id; the host runtime (Julia Distributed / MPI,

@@ -34,21 +34,31 @@ int32_t require_ctx() {
     return MOR_OK;
 }
 
+// Small work buffers come from the stream-ordered pool (cudaMallocAsync): a plain
+// cudaMalloc/cudaFree pair costs ~25 ms each next to a 100+ GB allocation (measured: 300 ms of
+// a 980 ms POD step), the pool costs microseconds and never synchronises the device.
+static constexpr size_t POOL_LIMIT = size_t(256) << 20;
+
 int32_t DevBuf::alloc(size_t nbytes) {
     release();
     if (nbytes == 0) nbytes = 8;
-    cudaError_t e = cudaMalloc(&p, nbytes);
+    pooled = nbytes <= POOL_LIMIT && g_ctx.ready;
+    cudaError_t e = pooled ? cudaMallocAsync(&p, nbytes, g_ctx.stream) : cudaMalloc(&p, nbytes);
     if (e != cudaSuccess) {
         p = nullptr;
-        return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+        return cuda_fail(e, pooled ? "cudaMallocAsync" : "cudaMalloc", __FILE__, __LINE__);
     }
     bytes = nbytes;
     return MOR_OK;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) {
+        if (pooled && g_ctx.ready) cudaFreeAsync(p, g_ctx.stream);
+        else cudaFree(p);
+    }
     p = nullptr;
     bytes = 0;
+    pooled = false;
 }
 
 int32_t scratch(size_t bytes, void** out) {
@@ -138,6 +148,14 @@ int32_t mor_b200_init(int32_t device) {
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
     MOR_CUDA(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
     g_ctx.stream = g_ctx.own_stream;
+    {   // keep up to 2 GB of freed work buffers cached in the default pool
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = uint64_t(2) << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     g_ctx.device = device;
     g_ctx.num_sms = prop.multiProcessorCount;
     g_ctx.ready = true;
@@ -171,6 +189,24 @@ int32_t mor_b200_set_stream(void* cuda_stream) {
 int32_t mor_b200_sync(void) {
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+int32_t mor_b200_host_alloc(uint64_t bytes, void** out) {
+    MOR_ARG(out != nullptr, "mor_b200_host_alloc: null output pointer");
+    MOR_TRY(require_ctx());
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes > 0 ? (size_t)bytes : 8, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
+    }
+    *out = p;
+    return MOR_OK;
+}
+
+int32_t mor_b200_host_free(void* p) {
+    if (p) MOR_CUDA(cudaFreeHost(p));
     return MOR_OK;
 }
 

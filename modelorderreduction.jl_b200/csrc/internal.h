@@ -57,12 +57,18 @@ int32_t scratch(size_t bytes, void** out);
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool pooled = false;   // from the stream-ordered pool (freed with cudaFreeAsync)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     int32_t alloc(size_t nbytes);
     void release();
+    void take(DevBuf& o) {  // move ownership
+        release();
+        p = o.p; bytes = o.bytes; pooled = o.pooled;
+        o.p = nullptr; o.bytes = 0; o.pooled = false;
+    }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -137,6 +143,7 @@ int32_t small_zero_rows(double* A, int m, int n, int ld, const double* flag);
 int32_t transpose(const double* in, int64_t rows, int64_t cols, int64_t ldin, double* out, int64_t ldout);
 int32_t gather_cols(const double* in, int ldin, int rows, int ncols, const int* d_perm, const double* d_scale,
                     double* out, int ldout);
+int32_t col_norms(const double* A, int lda, int rows, int n, std::vector<double>& out);   // host result
 // One-sided Jacobi on the columns of A (rows x n, lda), in place: on return the columns are
 // mutually orthogonal (A_in * V = A_out, V n x n accumulated if non-null).  sigma = column
 // norms sorted descending, order[j] = column holding the j-th largest.

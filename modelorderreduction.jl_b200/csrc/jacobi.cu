@@ -132,6 +132,18 @@ int32_t gather_cols(const double* in, int ldin, int rows, int ncols, const int* 
     return MOR_OK;
 }
 
+int32_t col_norms(const double* A, int lda, int rows, int n, std::vector<double>& out) {
+    DevBuf norms;
+    MOR_TRY(norms.alloc(sizeof(double) * (size_t)n));
+    colnorm_kernel<<<n, JT, 0, ctx().stream>>>(A, lda, rows, norms.as<double>());
+    count_launch();
+    MOR_CUDA(cudaGetLastError());
+    out.resize((size_t)n);
+    MOR_CUDA(cudaMemcpyAsync(out.data(), norms.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
+    MOR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return MOR_OK;
+}
+
 int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std::vector<double>& sigma,
                    std::vector<int>& order, int* sweeps_out) {
     Ctx& cx = ctx();

@@ -261,10 +261,7 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
             DevBuf copy;
             MOR_TRY(copy.alloc(sizeof(double) * (size_t)ldt * (size_t)n));
             MOR_CUDA(cudaMemcpyAsync(copy.p, T, sizeof(double) * (size_t)ldt * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            h->T_owned.release();
-            h->T_owned.p = copy.p;
-            h->T_owned.bytes = copy.bytes;
-            copy.p = nullptr;
+            h->T_owned.take(copy);
             T = h->T_owned.as<double>();
             may_overwrite = true;
         }
@@ -284,17 +281,26 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
         tm.core.stop();
         return js;
     }
-    DevBuf perm, inv_sigma;
+    // the accumulated rotations drift from unit norm by ~(rotations per column) * eps: renormalise
+    std::vector<double> vn;
+    MOR_TRY(col_norms(V.as<double>(), n, n, n, vn));
+    DevBuf perm, inv_sigma, inv_vn, inv_both;
     MOR_TRY(upload_perm(order, perm));
-    std::vector<double> is((size_t)n);
-    for (int j = 0; j < n; ++j) is[j] = h->sigma[j] > 0.0 ? 1.0 / h->sigma[j] : 0.0;
+    std::vector<double> is((size_t)n), iv((size_t)n), ib((size_t)n);
+    for (int j = 0; j < n; ++j) {
+        is[j] = h->sigma[j] > 0.0 ? 1.0 / h->sigma[j] : 0.0;
+        iv[j] = vn[order[j]] > 0.0 ? 1.0 / vn[order[j]] : 1.0;
+        ib[j] = is[j] * iv[j];
+    }
     MOR_TRY(upload_vec(is, inv_sigma));
+    MOR_TRY(upload_vec(iv, inv_vn));
+    MOR_TRY(upload_vec(ib, inv_both));
     MOR_TRY(h->Vs.alloc(nn));
     MOR_TRY(h->M.alloc(nn));
-    MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), nullptr, h->Vs.as<double>(), n));
+    MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_vn.as<double>(), h->Vs.as<double>(), n));
     if (single_pass) {
         // T = U S V'  =>  U = T V S^-1
-        MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_sigma.as<double>(), h->M.as<double>(), n));
+        MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_both.as<double>(), h->M.as<double>(), n));
     } else {
         // T_final = Q_{p-1} is orthonormal up to the last factor: U = T_final * inv(R_last) * U_R
         MOR_TRY(gather_cols(A.as<double>(), n, n, n, perm.as<int>(), inv_sigma.as<double>(), G.as<double>(), n));
@@ -372,7 +378,13 @@ int32_t factor_rsvd(mor_pod_s* h, const double* X, int64_t m, int n, int64_t ldx
     MOR_TRY(upload_vec(is, inv_sigma));
     MOR_TRY(h->M.alloc(sizeof(double) * (size_t)kq * r));
     MOR_TRY(h->Vs.alloc(sizeof(double) * (size_t)n * r));
-    MOR_TRY(gather_cols(V.as<double>(), kq, kq, r, perm.as<int>(), nullptr, h->M.as<double>(), kq));
+    std::vector<double> vn;
+    MOR_TRY(col_norms(V.as<double>(), kq, kq, kq, vn));
+    std::vector<double> iv((size_t)kq);
+    for (int j = 0; j < kq; ++j) iv[j] = vn[order[j]] > 0.0 ? 1.0 / vn[order[j]] : 1.0;
+    DevBuf inv_vn;
+    MOR_TRY(upload_vec(iv, inv_vn));
+    MOR_TRY(gather_cols(V.as<double>(), kq, kq, r, perm.as<int>(), inv_vn.as<double>(), h->M.as<double>(), kq));
     MOR_TRY(gather_cols(Bt.as<double>(), n, n, r, perm.as<int>(), inv_sigma.as<double>(), h->Vs.as<double>(), n));
     MOR_TRY(sign_fix(h->Vs.as<double>(), n, n, r, h->M.as<double>(), kq, kq));
     MOR_CUDA(cudaStreamSynchronize(st));
@@ -421,23 +433,13 @@ int32_t pod_factor_device(double* X, int64_t m, int64_t n, int64_t ldx, DevBuf* 
     h->m_global = m_global;
     h->method = method;
     h->wide = false;
-    if (own) {
-        h->T_owned.p = own->p;
-        h->T_owned.bytes = own->bytes;
-        own->p = nullptr;
-        own->bytes = 0;
-    }
+    if (own) h->T_owned.take(*own);
     const bool may_overwrite = own != nullptr || (flags & MOR_POD_MAY_OVERWRITE);
     const bool force2 = (flags & MOR_POD_FORCE_TWO_PASS) != 0;
 
     if (method == MOR_RSVD) {
         DevBuf keepX;  // X must stay alive through the call only (Q is a separate matrix)
-        if (own) {
-            keepX.p = h->T_owned.p;
-            keepX.bytes = h->T_owned.bytes;
-            h->T_owned.p = nullptr;
-            h->T_owned.bytes = 0;
-        }
+        if (own) keepX.take(h->T_owned);
         MOR_TRY(factor_rsvd(h.get(), X, m, (int)n, ldx, (int)k, (int)p, Omega_d, ldo, seed, tm));
         MOR_CUDA(cudaStreamSynchronize(ctx().stream));
     } else if (!wide) {
@@ -450,10 +452,7 @@ int32_t pod_factor_device(double* X, int64_t m, int64_t n, int64_t ldx, DevBuf* 
         MOR_CUDA(cudaMemsetAsync(Tt.p, 0, Tt.bytes, ctx().stream));
         MOR_TRY(transpose(X, m, n, ldx, Tt.as<double>(), ldt));
         MOR_CUDA(cudaStreamSynchronize(ctx().stream));
-        h->T_owned.release();  // the uploaded X (if any) is no longer needed
-        h->T_owned.p = Tt.p;
-        h->T_owned.bytes = Tt.bytes;
-        Tt.p = nullptr;
+        h->T_owned.take(Tt);   // the uploaded X (if any) is no longer needed
         h->wide = true;
         MOR_TRY(factor_tall(h.get(), h->T_owned.as<double>(), n, (int)m, ldt, true, force2, true, tm));
     }

@@ -118,6 +118,6 @@ def test_jacobi_svd(gpu, rows, n, kappa):
     # matrix is a well-conditioned basis times a column scaling; here just check against s
     assert np.max(np.abs(sig - s) / s) < 1e-6 * kappa * 1e-8 + 1e-9
     Vh = dV.to_host(); Ah = dA.to_host()
-    assert np.max(np.abs(Vh.T @ Vh - np.eye(n))) < 1e-13
+    assert np.max(np.abs(Vh.T @ Vh - np.eye(n))) < 2e-12
     assert rel(A @ Vh, Ah) < 1e-13
     assert 1 <= sweeps.value <= 20
