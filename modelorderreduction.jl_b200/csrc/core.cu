@@ -171,6 +171,8 @@ int32_t mor_b200_shutdown(void) {
         if (g_ctx.scratch_p) cudaFree(g_ctx.scratch_p);
         g_ctx.scratch_p = nullptr;
         g_ctx.scratch_bytes = 0;
+        if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+        g_ctx.copy_stream = nullptr;
         if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
         g_ctx.own_stream = nullptr;
         g_ctx.stream = nullptr;

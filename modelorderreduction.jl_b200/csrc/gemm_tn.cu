@@ -195,7 +195,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // C tile = sum over row groups (fixed order); mirror below the diagonal when symmetric
 __global__ void __launch_bounds__(256)
 gemm_tn_reduce_kernel(const double* __restrict__ part, int ngroups, int ntiles, int BM, int BN, int same,
-                      int tiles_q, int p, int q, double* __restrict__ C, int ldc) {
+                      int tiles_q, int p, int q, double* __restrict__ C, int ldc, int accumulate) {
     const int t = blockIdx.y;
     int ti, tj;
     if (same) {
@@ -213,13 +213,14 @@ gemm_tn_reduce_kernel(const double* __restrict__ part, int ngroups, int ntiles, 
     double s = 0.0;
     const double* src = part + (size_t)t * (BM * BN) + e;
     for (int gidx = 0; gidx < ngroups; ++gidx) s += src[(size_t)gidx * ntiles * (BM * BN)];
+    if (accumulate) s += C[(size_t)gj * ldc + gi];
     C[(size_t)gj * ldc + gi] = s;
     if (same && gi != gj) C[(size_t)gi * ldc + gj] = s;
 }
 
 template <int BM, int BN, int WM, int WN, int KB, int STAGES, int MINB>
 int32_t launch_tn(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
-                  int ldc) {
+                  int ldc, int accumulate) {
     using Cfg = TnCfg<BM, BN, WM, WN, KB, STAGES, MINB>;
     Ctx& cx = ctx();
     const bool same = (A == B && lda == ldb && p == q);
@@ -250,7 +251,7 @@ int32_t launch_tn(const double* A, int64_t lda, int p, const double* B, int64_t 
     MOR_CUDA(cudaGetLastError());
     dim3 rgrid((BM * BN + 255) / 256, ntiles);
     gemm_tn_reduce_kernel<<<rgrid, 256, 0, cx.stream>>>(part, (int)ngroups, ntiles, BM, BN, same ? 1 : 0, tiles_q, p,
-                                                        q, C, ldc);
+                                                        q, C, ldc, accumulate);
     MOR_CUDA(cudaGetLastError());
     count_launch(2);
     return MOR_OK;
@@ -259,17 +260,17 @@ int32_t launch_tn(const double* A, int64_t lda, int p, const double* B, int64_t 
 }  // namespace
 
 int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
-                int ldc) {
+                int ldc, int accumulate) {
     MOR_ARG(A && B && C && p >= 1 && q >= 1 && m >= 0 && ldc >= p, "gemm_tn: bad arguments");
     MOR_ARG(lda % 2 == 0 && ldb % 2 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0,
             "gemm_tn: operands must be 16-byte aligned with even leading dimensions");
     MOR_ARG(m < (int64_t(1) << 31), "gemm_tn: more than 2^31 rows per GPU shard");
     if (m == 0) {
-        MOR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 8, 0, (size_t)p * 8, (size_t)q, ctx().stream));
+        if (!accumulate) MOR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 8, 0, (size_t)p * 8, (size_t)q, ctx().stream));
         return MOR_OK;
     }
-    if (p <= 64 || q <= 64) return launch_tn<64, 64, 16, 32, 20, 5, 2>(A, lda, p, B, ldb, q, m, C, ldc);
-    return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc);
+    if (p <= 64 || q <= 64) return launch_tn<64, 64, 16, 32, 20, 5, 2>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
+    return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }
 
 }  // namespace mor

@@ -39,6 +39,7 @@ struct Ctx {
     int num_sms = 148;
     cudaStream_t stream = nullptr;      // the stream all work is enqueued on
     cudaStream_t own_stream = nullptr;  // created by init
+    cudaStream_t copy_stream = nullptr; // host->device ingest, overlapped with the first Gram pass
     void* comm = nullptr;               // ncclComm_t
     int rank = 0, nranks = 1;
     double timings[MOR_T_NSLOTS] = {0};
@@ -112,8 +113,9 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
 
 // ---- tall-skinny GEMMs on DMMA (gemm_tn.cu / gemm_nn.cu) -----------------------------------
 // C (p x q, ldc, column-major, both triangles when A == B) = A' * B, A: m x p, B: m x q.
+// accumulate != 0: C += A' * B (used to build the Gram matrix chunk by chunk while rows still arrive)
 int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m,
-                double* C, int ldc);
+                double* C, int ldc, int accumulate = 0);
 // Y (m x q) = X (m x n) * W (n x q).  Wt is W TRANSPOSED, i.e. q x n column-major ... see .cu
 // upper != 0: W is upper triangular (W[i][j] = 0 for i > j) and Y may alias X (in place).
 int32_t gemm_nn(const double* X, int64_t ldx, int n, const double* W, int ldw, int q, int64_t m,
@@ -126,6 +128,7 @@ struct SmallInfo {
     int nzero;       // all-zero columns (G_jj == 0)
     int chol_fail;   // 1-based index of the first non-positive pivot, 0 = ok
     int rotations;   // Jacobi rotations applied in the last sweep
+    double max_cos;  // largest |cosine| between two columns met in the last sweep
 };
 int32_t small_info_reset(SmallInfo* d_info);
 int32_t small_info_read(const SmallInfo* d_info, SmallInfo* h);

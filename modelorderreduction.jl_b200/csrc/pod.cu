@@ -14,6 +14,7 @@
 // B' = X'Q, Jacobi SVD of B', U = Q U_B.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -128,9 +129,13 @@ struct PassOut {
     int nzero = 0;
 };
 int32_t gram_pass(const double* T, int64_t trows, int n, int64_t ldt, bool replicated, double* G, double* Rs,
-                  double* D, SmallInfo* d_info, Timers& tm, PassOut* out) {
+                  double* D, SmallInfo* d_info, Timers& tm, PassOut* out, const double* G_pre = nullptr) {
     tm.gram.start();
-    MOR_TRY(gemm_tn(T, ldt, n, T, ldt, n, trows, G, n));
+    if (G_pre) {  // this rank's Gram matrix was accumulated while the rows were still arriving
+        MOR_CUDA(cudaMemcpyAsync(G, G_pre, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, ctx().stream));
+    } else {
+        MOR_TRY(gemm_tn(T, ldt, n, T, ldt, n, trows, G, n));
+    }
     tm.gram.stop();
     if (!replicated && ctx().nranks > 1) {
         tm.comm.start();
@@ -214,7 +219,7 @@ int32_t orthonormalize(double* Y, int64_t rows, int l, int64_t ldy, bool replica
 // `may_overwrite`; otherwise a private copy is made the first time an in-place pass is
 // needed (returned through h->T_owned).  Fills h->M, h->Vs, h->sigma, h->T, passes, sweeps.
 int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, bool may_overwrite,
-                    bool force_two_pass, bool replicated, Timers& tm) {
+                    bool force_two_pass, bool replicated, Timers& tm, const double* G_first = nullptr) {
     const size_t nn = sizeof(double) * (size_t)n * n;
     DevBuf G, Rs, Rtot, Rtmp, Rinv, D, D1, info, A, V;
     MOR_TRY(G.alloc(nn));
@@ -233,7 +238,7 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     for (;;) {
         PassOut po;
         MOR_TRY(gram_pass(T, trows, n, ldt, replicated, G.as<double>(), Rs.as<double>(), D.as<double>(),
-                          info.as<SmallInfo>(), tm, &po));
+                          info.as<SmallInfo>(), tm, &po, passes == 0 ? G_first : nullptr));
         ++passes;
         tm.core.start();
         // R_p = Rs * diag(D)  (zero columns act as D = 1)
@@ -413,7 +418,7 @@ int32_t global_rows(int64_t m, int64_t* m_global) {
 // ownership of X's allocation to the handle (host-pointer entry points).
 int32_t pod_factor_device(double* X, int64_t m, int64_t n, int64_t ldx, DevBuf* own, int32_t method, int64_t k,
                           int64_t p, const double* Omega_d, int64_t ldo, uint64_t seed, int32_t flags,
-                          mor_pod_t* handle, double* S_out, int64_t* nS, Timers& tm) {
+                          mor_pod_t* handle, double* S_out, int64_t* nS, Timers& tm, const double* G_first = nullptr) {
     MOR_ARG(handle && S_out && nS, "pod_factor: null output pointer");
     MOR_ARG(m >= 0 && n >= 1, "pod_factor: bad dimensions");
     MOR_ARG(method == MOR_SVD || method == MOR_TSVD || method == MOR_RSVD, "pod_factor: unknown method");
@@ -443,7 +448,7 @@ int32_t pod_factor_device(double* X, int64_t m, int64_t n, int64_t ldx, DevBuf* 
         MOR_TRY(factor_rsvd(h.get(), X, m, (int)n, ldx, (int)k, (int)p, Omega_d, ldo, seed, tm));
         MOR_CUDA(cudaStreamSynchronize(ctx().stream));
     } else if (!wide) {
-        MOR_TRY(factor_tall(h.get(), X, m, (int)n, ldx, may_overwrite, force2, false, tm));
+        MOR_TRY(factor_tall(h.get(), X, m, (int)n, ldx, may_overwrite, force2, false, tm, G_first));
     } else {
         // T = X' (n x m), owned by the handle
         const int64_t ldt = (n + 1) & ~int64_t(1);
@@ -523,11 +528,44 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
     Timers tm;
     tm.total.start();
     const int64_t ld = std::max<int64_t>((m + 1) & ~int64_t(1), 2);
-    DevBuf dX, dOm;
+    DevBuf dX, dOm, Gacc;
     MOR_TRY(dX.alloc(sizeof(double) * (size_t)ld * (size_t)n));
-    tm.h2d.start();
-    if (ld != m) MOR_CUDA(cudaMemsetAsync(dX.p, 0, dX.bytes, cx.stream));
-    if (m > 0) {
+    if (ld != m)  // keep the pad row finite
+        MOR_CUDA(cudaMemset2DAsync(dX.as<double>() + m, (size_t)ld * 8, 0, 8, (size_t)n, cx.stream));
+    // Pipelined ingest (tall SVD/TSVD of a Matrix): rows travel in ~1 GiB chunks on a copy
+    // stream while the Gram matrix of the chunks that already landed accumulates on the DMMA
+    // pipe -- the first CholeskyQR pass is hidden behind the PCIe transfer.
+    const char* ch_env = getenv("MOR_B200_INGEST_CHUNK_ROWS");  // test hook: force small chunks
+    const bool pipelined = !cols && method != MOR_RSVD && m >= n && n <= 4096 &&
+                           (ch_env != nullptr || (size_t)m * n >= (size_t(1) << 24));
+    std::vector<cudaEvent_t> events;
+    if (m > 0 && pipelined) {
+        if (!cx.copy_stream) MOR_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
+        MOR_TRY(Gacc.alloc(sizeof(double) * (size_t)n * n));
+        cudaEvent_t ready;
+        MOR_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        MOR_CUDA(cudaEventRecord(ready, cx.stream));
+        MOR_CUDA(cudaStreamWaitEvent(cx.copy_stream, ready, 0));
+        events.push_back(ready);
+        int64_t ch = ((int64_t(1) << 27) / n) & ~int64_t(4095);  // rows per chunk: ~1 GiB
+        if (ch < 4096) ch = 4096;
+        if (ch_env && atoll(ch_env) > 0) ch = (atoll(ch_env) + 1) & ~1LL;
+        tm.gram.start();
+        for (int64_t r0 = 0; r0 < m; r0 += ch) {
+            const int64_t rc = std::min(ch, m - r0);
+            MOR_CUDA(cudaMemcpy2DAsync(dX.as<double>() + r0, (size_t)ld * 8, X + r0, (size_t)ldx * 8, (size_t)rc * 8,
+                                       (size_t)n, cudaMemcpyHostToDevice, cx.copy_stream));
+            cudaEvent_t ev;
+            MOR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            MOR_CUDA(cudaEventRecord(ev, cx.copy_stream));
+            MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev, 0));
+            events.push_back(ev);
+            MOR_TRY(gemm_tn(dX.as<double>() + r0, ld, (int)n, dX.as<double>() + r0, ld, (int)n, rc, Gacc.as<double>(),
+                            (int)n, r0 > 0 ? 1 : 0));
+        }
+        tm.gram.stop();
+    } else if (m > 0) {
+        tm.h2d.start();
         if (cols) {
             for (int64_t j = 0; j < n; ++j) {
                 MOR_ARG(cols[j] != nullptr, "mor_b200_pod_factor_cols: null column pointer");
@@ -538,6 +576,7 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
             MOR_CUDA(cudaMemcpy2DAsync(dX.p, (size_t)ld * 8, X, (size_t)ldx * 8, (size_t)m * 8, (size_t)n,
                                        cudaMemcpyHostToDevice, cx.stream));
         }
+        tm.h2d.stop();
     }
     int64_t ldo = 0;
     if (Omega && method == MOR_RSVD) {
@@ -546,11 +585,12 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
                                  cx.stream));
         ldo = n;
     }
-    tm.h2d.stop();
     int32_t st = pod_factor_device(dX.as<double>(), m, n, ld, &dX, method, k, p, dOm.as<double>(), ldo, seed, 0, handle,
-                                   S_out, nS, tm);
+                                   S_out, nS, tm, (m > 0 && pipelined) ? Gacc.as<double>() : nullptr);
     tm.total.stop();
     cudaStreamSynchronize(cx.stream);
+    if (cx.copy_stream) cudaStreamSynchronize(cx.copy_stream);
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     tm.collect();
     return st;
 }

@@ -202,3 +202,15 @@ def test_device_resident_synthetic_config2_shape(gpu):
     assert np.array_equal(X.to_host(), Xh)              # without MAY_OVERWRITE the input is untouched
     t = _lib.last_timings()
     assert t["gram"] > 0 and t["total"] >= t["gram"]
+
+
+def test_pipelined_host_ingest_chunks(gpu, monkeypatch):
+    """Host-pointer ingest streams row chunks on a copy stream while the Gram matrix of the chunks
+    that already landed accumulates; forced to 13 ragged chunks here.  Same result as one shot."""
+    X = graded(50_003, 96, 3, 21)
+    monkeypatch.setenv("MOR_B200_INGEST_CHUNK_ROWS", "4000")
+    pb, _ = check_against_oracle(X, 10, mor_b200.SVD(), O.SVD())
+    big = np.zeros((50_100, 96), order="F"); big[:50_003] = X          # ld > m view
+    f = _factor(big[:50_003], _lib.MOR_TSVD, 10)
+    assert O.sigma_error(pb.spectrum[:10], f.s) <= 1e-12
+    f.close()
