@@ -6,8 +6,8 @@
 // A sweep is n-1 rounds of a round-robin tournament; the n/2 column pairs of a round are
 // disjoint and rotated concurrently, one CTA per pair: three dot products (a, b, c), the
 // rotation that zeroes c, applied to the two columns of A and of the accumulated V.  The
-// rotation threshold is |c| <= tol * sqrt(a b) with tol = sqrt(rows) * eps (as in LAPACK's
-// dgesvj), which gives the singular values to high relative accuracy.
+// rotation threshold is |c| <= tol * sqrt(a b) with tol = rows * eps, which gives the singular
+// values to high relative accuracy (the neglected cosines enter sigma only at second order).
 //
 // A whole sweep is ONE cooperative launch: the CTAs stay resident, keep the four columns of
 // a pair in registers between the dot products and the rotation (one L2 round trip instead
@@ -272,7 +272,11 @@ int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std:
     SmallInfo* d_info = info_buf.as<SmallInfo>();
     if (V) MOR_TRY(small_identity(V, n, ldv));
     const int n_even = (n + 1) & ~1;
-    const double tol = sqrt((double)rows) * 2.220446049250313e-16;
+    // rotate while |cos(a_p, a_q)| > tol.  dgesvj uses sqrt(rows)*eps; the computed dot product of a
+    // tiny and a large column carries rounding noise of about that size, which keeps triggering
+    // rotations for tens of sweeps on graded matrices (30 sweeps at 256 x 256, kappa 1e8), so the
+    // threshold sits a factor sqrt(rows) above the noise.  Effect on sigma is second order (tol^2).
+    const double tol = (double)(rows > 64 ? rows : 64) * 2.220446049250313e-16;
     int sweeps = 0;
     const int max_sweeps = 40;
     bool converged = (n == 1);

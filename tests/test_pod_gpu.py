@@ -214,3 +214,20 @@ def test_pipelined_host_ingest_chunks(gpu, monkeypatch):
     f = _factor(big[:50_003], _lib.MOR_TSVD, 10)
     assert O.sigma_error(pb.spectrum[:10], f.s) <= 1e-12
     f.close()
+
+
+def test_fitzhugh_nagumo_pod5_deim5(gpu):
+    """BASELINE config 1: FitzHugh-Nagumo MOL N=15 (32-dim), POD5-DEIM5 as deim(sys, snapshot, 5;
+    deim_dim=5) does numerically (deim.jl:223-225,245-249,147): TSVD POD of the 32 x nt snapshots,
+    TSVD POD of the nonlinear snapshots, DEIM indices of the latter -- wide matrices throughout."""
+    import fhn_fixture as F
+    X = F.snapshots()
+    assert X.shape == (32, 1401)
+    pb, po = check_against_oracle(X, 5, mor_b200.TSVD(), O.TSVD())          # V = pod_reducer.rbasis
+    assert pb.rbasis.shape == (32, 5)
+    NL = F.nonlinear_snapshots(X)[:16]                                        # the 16 v-equations carry f(v)
+    ub, uo = check_against_oracle(NL, 5, mor_b200.TSVD(), O.TSVD())          # U = deim_reducer.rbasis
+    idx = mor_b200.deim_interpolation_indices(ub.rbasis)
+    assert idx.tolist() == O.deim_interpolation_indices(ub.rbasis).tolist()
+    assert idx.tolist() == O.deim_interpolation_indices(uo.rbasis * np.sign((uo.rbasis * ub.rbasis).sum(0))).tolist()
+    assert len(set(idx.tolist())) == 5 and 1 <= idx.min() and idx.max() <= 16
