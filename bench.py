@@ -277,7 +277,7 @@ def run_ours(args):
     lib.mor_dbg_gemm_tn.restype = C.c_int32
     UtU = DeviceMatrix.alloc(k, k)
     _lib.check(lib.mor_dbg_gemm_tn(U.handle, U.handle, UtU.handle))
-    g = torch.from_numpy(UtU.to_host()).cuda()
+    g = torch.from_numpy(np.ascontiguousarray(UtU.to_host())).cuda()
     if world > 1:
         dist.all_reduce(g)
     orth_err = float((g - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item())
@@ -356,6 +356,9 @@ def run_ours(args):
                          "live_read_peak_gbs": pk_g.value, "traffic": None},
             "tail_ms": dacc["deim_tail"] / args.steps}
     B.free()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return

@@ -274,27 +274,36 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     }
 
     // ---- core SVD of the n x n factor -----------------------------------------------------
+    // R = U_R S V'.  When the POD basis comes from the tall side (U = T_final * inv(R_last) * U_R)
+    // the rotations need not be accumulated: the Jacobi sweeps then move half the data, and the
+    // right vectors are recovered as V = R' U_R S^-1 (accurate to eps * s_1 / s_j -- they are
+    // only an optional output there).  For a wide input the small-side vectors ARE the basis, so
+    // V is accumulated and stays orthonormal to rounding for every column.
     tm.core.start();
+    const bool accumulate_v = replicated || n < 64;
     MOR_TRY(A.alloc(nn));
     MOR_CUDA(cudaMemcpyAsync(A.p, Rtot.p, nn, cudaMemcpyDeviceToDevice, st));
     // rows of R that belong to all-zero snapshot columns carry no energy
     MOR_TRY(small_zero_rows(A.as<double>(), n, n, n, D1.as<double>()));
+    if (!accumulate_v) MOR_CUDA(cudaMemcpyAsync(Rtot.p, A.p, nn, cudaMemcpyDeviceToDevice, st));  // keep R (deflated)
     std::vector<int> order;
     int sweeps = 0;
-    int32_t js = jacobi_svd(A.as<double>(), n, n, n, V.as<double>(), n, h->sigma, order, &sweeps);
+    int32_t js = jacobi_svd(A.as<double>(), n, n, n, accumulate_v ? V.as<double>() : nullptr, n, h->sigma, order, &sweeps);
     if (js != MOR_OK) {
         tm.core.stop();
         return js;
     }
-    // the accumulated rotations drift from unit norm by ~(rotations per column) * eps: renormalise
-    std::vector<double> vn;
-    MOR_TRY(col_norms(V.as<double>(), n, n, n, vn));
     DevBuf perm, inv_sigma, inv_vn, inv_both;
     MOR_TRY(upload_perm(order, perm));
-    std::vector<double> is((size_t)n), iv((size_t)n), ib((size_t)n);
+    std::vector<double> is((size_t)n), iv((size_t)n, 1.0), ib((size_t)n);
+    if (accumulate_v) {
+        // the accumulated rotations drift from unit norm by ~(rotations per column) * eps: renormalise
+        std::vector<double> vn;
+        MOR_TRY(col_norms(V.as<double>(), n, n, n, vn));
+        for (int j = 0; j < n; ++j) iv[j] = vn[order[j]] > 0.0 ? 1.0 / vn[order[j]] : 1.0;
+    }
     for (int j = 0; j < n; ++j) {
         is[j] = h->sigma[j] > 0.0 ? 1.0 / h->sigma[j] : 0.0;
-        iv[j] = vn[order[j]] > 0.0 ? 1.0 / vn[order[j]] : 1.0;
         ib[j] = is[j] * iv[j];
     }
     MOR_TRY(upload_vec(is, inv_sigma));
@@ -302,16 +311,23 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     MOR_TRY(upload_vec(ib, inv_both));
     MOR_TRY(h->Vs.alloc(nn));
     MOR_TRY(h->M.alloc(nn));
-    MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_vn.as<double>(), h->Vs.as<double>(), n));
-    if (single_pass) {
+    if (accumulate_v) {
+        MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_vn.as<double>(), h->Vs.as<double>(), n));
+    }
+    if (single_pass && accumulate_v) {
         // T = U S V'  =>  U = T V S^-1
         MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_both.as<double>(), h->M.as<double>(), n));
     } else {
-        // T_final = Q_{p-1} is orthonormal up to the last factor: U = T_final * inv(R_last) * U_R
+        // T_final (X itself after one pass, Q_{p-1} otherwise) times inv(R_last) is orthonormal:
+        // U = T_final * inv(R_last) * U_R with U_R = A S^-1
         MOR_TRY(gather_cols(A.as<double>(), n, n, n, perm.as<int>(), inv_sigma.as<double>(), G.as<double>(), n));
         MOR_TRY(small_trinv_upper(Rs.as<double>(), n, n, Rinv.as<double>(), n));
         MOR_TRY(small_scale_rc(Rinv.as<double>(), n, n, n, D.as<double>(), /*rows=*/true, /*inv=*/true));
         MOR_TRY(small_gemm(false, false, n, n, n, 1.0, Rinv.as<double>(), n, G.as<double>(), n, 0.0, h->M.as<double>(), n));
+        if (!accumulate_v) {  // V = R' U_R S^-1
+            MOR_TRY(small_gemm(true, false, n, n, n, 1.0, Rtot.as<double>(), n, G.as<double>(), n, 0.0, h->Vs.as<double>(), n));
+            MOR_TRY(small_scale_rc(h->Vs.as<double>(), n, n, n, inv_sigma.as<double>(), /*rows=*/false, /*inv=*/false));
+        }
     }
     MOR_TRY(sign_fix(h->Vs.as<double>(), n, n, n, h->M.as<double>(), n, n));
     MOR_CUDA(cudaStreamSynchronize(st));  // perm / inv_sigma are released on return
