@@ -18,10 +18,16 @@
 // second kernel (deterministic, no atomics) which also mirrors the lower triangle.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
 namespace mor {
+
+int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
+                        int ldc, int accumulate);  // gemm_tn_sk.cu
+
 namespace {
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -45,8 +51,10 @@ int32_t get_encode(EncodeTiledFn* fn) {
     return MOR_OK;
 }
 
+}  // namespace
+
 // tensor map over a column-major (rows x cols, ld) FP64 matrix; box = box_rows x box_cols
-int32_t make_map(const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+int32_t make_tensor_map(const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
                  CUtensorMap* out) {
     EncodeTiledFn enc = nullptr;
     MOR_TRY(get_encode(&enc));
@@ -64,6 +72,8 @@ int32_t make_map(const double* base, int64_t rows, int64_t cols, int64_t ld, int
     }
     return MOR_OK;
 }
+
+namespace {
 
 template <int BM, int BN, int WM, int WN, int KB, int STAGES, int MINB>
 struct TnCfg {
@@ -234,8 +244,8 @@ int32_t launch_tn(const double* A, int64_t lda, int p, const double* B, int64_t 
     if (ngroups > npanels) ngroups = npanels > 0 ? npanels : 1;
 
     CUtensorMap mapA, mapB;
-    MOR_TRY(make_map(A, m, p, lda, KB, BM, &mapA));
-    MOR_TRY(make_map(B, m, q, ldb, KB, BN, &mapB));
+    MOR_TRY(make_tensor_map(A, m, p, lda, KB, BM, &mapA));
+    MOR_TRY(make_tensor_map(B, m, q, ldb, KB, BN, &mapB));
 
     double* part = nullptr;
     MOR_TRY(scratch(sizeof(double) * (size_t)ngroups * ntiles * BM * BN, reinterpret_cast<void**>(&part)));
@@ -270,6 +280,11 @@ int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ld
         return MOR_OK;
     }
     if (p <= 64 || q <= 64) return launch_tn<64, 64, 16, 32, 20, 5, 2>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
+    // The balanced stream-K variant (gemm_tn_sk.cu) is kept as an opt-in experiment: measured on
+    // B200 at 16M x 1024 it is SLOWER (705 ms vs 565 ms) -- it gives up the lock-step L2 sharing of
+    // the row groups, re-reads the matrix 9x from HBM in 160-byte pieces and becomes DRAM-page bound.
+    static const bool streamk = getenv("MOR_B200_GEMM_TN_STREAMK") != nullptr;
+    if (streamk) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
     return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }
 

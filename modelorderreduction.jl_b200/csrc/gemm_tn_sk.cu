@@ -1,0 +1,288 @@
+// gemm_tn, balanced ("stream-K") variant for outputs wider than 64 columns.  EXPERIMENT, off by
+// default (MOR_B200_GEMM_TN_STREAMK=1 enables it): correct (all parity tests pass with it) but
+// measured slower than the lock-step decomposition on B200, see the note at the end of this comment.
+//
+// The plain decomposition of gemm_tn.cu -- one CTA per (128 x 128 tile, row group), 36 upper
+// tiles x 4 groups = 144 CTAs at n = 1024 -- runs the DMMA pipe at ~100% on the SMs it uses (ncu:
+// sm__pipe_tensor_subpipe_dmma_cycles_active 97.3% = 144/148), but leaves 4 SMs idle and computes
+// the useless lower halves of the 8 diagonal tiles.  Here the (tile x row panel) work space is
+// flattened and cut into one equal-cost contiguous piece per SM:
+//   * off-diagonal tiles are 128 x 128 (8 warps x 32 x 64 register tiles), cost 4 per panel;
+//   * a diagonal 128 x 128 block is three 64 x 64 tiles (two on the diagonal, one above), 8 warps x
+//     16 x 32, cost 1 per panel each -- 25% less work than the full block;
+//   * every CTA walks its piece: for each segment (tile, panel range) it zeroes its accumulators,
+//     streams the panels through the same TMA ring as gemm_tn.cu (one elected producer lane,
+//     PREFETCH panels ahead, running across segment boundaries), and writes a partial tile;
+//   * a second kernel adds the partial tiles of every tile in a fixed order (deterministic) and
+//     mirrors the lower triangle.
+// A panel is now read from HBM by every tile that needs it (9x the matrix at n = 1024) instead of
+// once via L2 -- the price of balance.  MEASURED (B200, 16M x 1024): 705 ms vs 565 ms for the
+// lock-step kernel.  The 9x traffic arrives as 160-byte column pieces 134 MB apart, i.e. one DRAM row
+// activation per piece, and HBM delivers only ~1.8 TB/s of it: the kernel turns DRAM-bound.  Kept for
+// a later round (taller panels / a panel-blocked internal layout would be needed to make it pay).
+#include <cuda.h>
+
+#include <vector>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mor {
+
+int32_t make_tensor_map(const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                        CUtensorMap* out);  // gemm_tn.cu
+
+namespace {
+
+constexpr int KB = 20, STAGES = 5, PREFETCH = STAGES - 2;
+constexpr int STAGE_DOUBLES = 256 * KB;  // room for two 128-column operand blocks
+constexpr size_t SK_SMEM = (size_t)STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 128;
+
+struct Seg {
+    int a_col, b_col;      // first column of the A / B operand block
+    int small;             // 0: 128 x 128 tile, 1: 64 x 64 tile
+    int diag;              // A block == B block (only one is loaded)
+    long long p_begin, p_end;
+    long long part_off;    // offset (doubles) of this segment's partial tile in the workspace
+};
+
+struct TileInfo {
+    int a_col, b_col, small, diag;
+    int seg_begin, seg_end;
+};
+
+struct Maps {
+    CUtensorMap a_big, b_big, a_small, b_small;
+};
+
+struct Producer {
+    const Maps* maps;
+    const Seg* segs;
+    double* ring;
+    uint64_t *full, *empty;
+    int seg;            // cursor: segment and panel of the next load
+    long long panel;
+
+    // load the j-th panel of this CTA's piece into stage j % STAGES
+    __device__ __forceinline__ void issue(long long j) {
+        const Seg sg = segs[seg];
+        const int s = (int)(j % STAGES);
+        const long long fill = j / STAGES;
+        if (fill > 0) ptx::mbar_wait(&empty[s], (uint32_t)((fill - 1) & 1));
+        double* dst = ring + (size_t)s * STAGE_DOUBLES;
+        const int bw = sg.small ? 64 : 128;
+        ptx::mbar_expect_tx(&full[s], (uint32_t)((sg.diag ? bw : 2 * bw) * KB * 8));
+        const int row = (int)(panel * KB);
+        ptx::tma_load_2d(dst, sg.small ? &maps->a_small : &maps->a_big, row, sg.a_col, &full[s]);
+        if (!sg.diag) ptx::tma_load_2d(dst + bw * KB, sg.small ? &maps->b_small : &maps->b_big, row, sg.b_col, &full[s]);
+        if (++panel == sg.p_end) {
+            ++seg;
+            panel = segs[seg].p_begin;  // segs[] ends with a sentinel entry
+        }
+    }
+};
+
+template <int WM, int WN, int BMT>
+__device__ __forceinline__ void run_segment(const Seg sg, double* ring, uint64_t* full, uint64_t* empty, int& stage,
+                                            uint32_t& phase, long long& consumed, long long np_total, bool producer,
+                                            Producer& prod, double* __restrict__ part) {
+    constexpr int MI = WM / 8, NJ = WN / 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm0 = (warp & 3) * WM, wn0 = (warp >> 2) * WN;
+    const int g = lane >> 2, tq = lane & 3;
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (long long p = sg.p_begin; p < sg.p_end; ++p) {
+        if (producer && consumed + PREFETCH < np_total) prod.issue(consumed + PREFETCH);
+        __syncwarp();
+        ptx::mbar_wait(&full[stage], phase);
+        const double* As = ring + (size_t)stage * STAGE_DOUBLES;
+        const double* Bs = sg.diag ? As : As + BMT * KB;
+        const double* ap = As + (wm0 + g) * KB + tq;
+        const double* bp = Bs + (wn0 + g) * KB + tq;
+#pragma unroll
+        for (int s = 0; s < KB / 4; ++s) {
+            double a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * KB + 4 * s];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = bp[j * 8 * KB + 4 * s];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) ptx::dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+        ++consumed;
+    }
+    double* out = part + sg.part_off;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int r = wm0 + 8 * i + g, c = wn0 + 8 * j + 2 * tq;
+            out[(size_t)c * BMT + r] = acc[i][j][0];
+            out[(size_t)(c + 1) * BMT + r] = acc[i][j][1];
+        }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tn_sk_kernel(const __grid_constant__ Maps maps, const Seg* __restrict__ segs, const int* __restrict__ cta_seg,
+                  double* __restrict__ part) {
+    extern __shared__ unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * STAGE_DOUBLES);
+    uint64_t* empty = full + STAGES;
+    const int s0 = cta_seg[blockIdx.x], s1 = cta_seg[blockIdx.x + 1];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 8);
+        }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    long long np_total = 0;
+    for (int s = s0; s < s1; ++s) np_total += segs[s].p_end - segs[s].p_begin;
+    const bool producer = (threadIdx.x == 0);
+    Producer prod{&maps, segs, ring, full, empty, s0, 0};
+    if (producer && s1 > s0) {
+        prod.panel = segs[s0].p_begin;
+        ptx::tma_prefetch_desc(&maps.a_big);
+        ptx::tma_prefetch_desc(&maps.b_big);
+        ptx::tma_prefetch_desc(&maps.a_small);
+        ptx::tma_prefetch_desc(&maps.b_small);
+        for (long long j = 0; j < PREFETCH && j < np_total; ++j) prod.issue(j);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    long long consumed = 0;
+    for (int s = s0; s < s1; ++s) {
+        const Seg sg = segs[s];
+        if (sg.small)
+            run_segment<16, 32, 64>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
+        else
+            run_segment<32, 64, 128>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const Seg* __restrict__ segs,
+                         const TileInfo* __restrict__ tiles, int same, int p, int q, double* __restrict__ C, int ldc,
+                         int accumulate) {
+    const TileInfo t = tiles[blockIdx.y];
+    const int bm = t.small ? 64 : 128;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= bm * bm) return;
+    const int r = e % bm, c = e / bm;
+    const int gi = t.a_col + r, gj = t.b_col + c;
+    if (gi >= p || gj >= q) return;
+    if (same && t.diag && r > c) return;  // written by the mirrored element: exact symmetry
+    double s = 0.0;
+    for (int sg = t.seg_begin; sg < t.seg_end; ++sg) s += part[segs[sg].part_off + e];
+    if (accumulate) s += C[(size_t)gj * ldc + gi];
+    C[(size_t)gj * ldc + gi] = s;
+    if (same && gi != gj) C[(size_t)gi * ldc + gj] = s;
+}
+
+}  // namespace
+
+// C (p x q) = A' * B, or the symmetric Gram matrix when A == B.  Requires p, q > 64.
+int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
+                        int ldc, int accumulate) {
+    Ctx& cx = ctx();
+    const bool same = (A == B && lda == ldb && p == q);
+    const long long P = (m + KB - 1) / KB;
+    // ---- tiles -------------------------------------------------------------------------------
+    std::vector<TileInfo> tiles;
+    const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
+    for (int ti = 0; ti < tp; ++ti)
+        for (int tj = same ? ti : 0; tj < tq_; ++tj) {
+            if (same && ti == tj) {
+                const int c0 = ti * 128;
+                tiles.push_back({c0, c0, 1, 1, 0, 0});
+                if (c0 + 64 < p) {
+                    tiles.push_back({c0, c0 + 64, 1, 0, 0, 0});
+                    tiles.push_back({c0 + 64, c0 + 64, 1, 1, 0, 0});
+                }
+            } else {
+                tiles.push_back({ti * 128, tj * 128, 0, 0, 0, 0});
+            }
+        }
+    // ---- equal-cost contiguous pieces, one per SM ----------------------------------------------
+    long long total = 0;
+    for (const TileInfo& t : tiles) total += (t.small ? 1 : 4) * P;
+    int nct = cx.num_sms;
+    if (total < (long long)nct * 16) nct = (int)std::max<long long>(1, total / 16);  // tiny problems: fewer CTAs
+    std::vector<Seg> segs;
+    std::vector<int> cta_seg(1, 0);
+    long long part_doubles = 0;
+    int cta = 0;
+    long long quota = (total + nct - 1) / nct, left = quota;
+    for (TileInfo& t : tiles) {
+        const int cost = t.small ? 1 : 4;
+        t.seg_begin = (int)segs.size();
+        long long pb = 0;
+        while (pb < P) {
+            const bool last = (cta + 1 >= nct);
+            if (!last && left < cost) {  // this CTA's share is used up: open the next one
+                cta_seg.push_back((int)segs.size());
+                ++cta;
+                left = quota;
+                continue;
+            }
+            const long long take = last ? (P - pb) : std::min(P - pb, left / cost);
+            segs.push_back({t.a_col, t.b_col, t.small, t.diag, pb, pb + take, part_doubles});
+            part_doubles += t.small ? 64 * 64 : 128 * 128;
+            pb += take;
+            left -= take * cost;
+        }
+        t.seg_end = (int)segs.size();
+    }
+    while ((int)cta_seg.size() < nct + 1) cta_seg.push_back((int)segs.size());
+    segs.push_back({0, 0, 0, 0, 0, 0, 0});  // sentinel for the producer cursor
+
+    Maps maps;
+    MOR_TRY(make_tensor_map(A, m, p, lda, KB, 128, &maps.a_big));
+    MOR_TRY(make_tensor_map(B, m, q, ldb, KB, 128, &maps.b_big));
+    MOR_TRY(make_tensor_map(A, m, p, lda, KB, 64, &maps.a_small));
+    MOR_TRY(make_tensor_map(B, m, q, ldb, KB, 64, &maps.b_small));
+
+    // workspace: partial tiles | segs | cta_seg | tiles
+    const size_t b_part = sizeof(double) * (size_t)part_doubles;
+    const size_t b_segs = (sizeof(Seg) * segs.size() + 255) & ~size_t(255);
+    const size_t b_cta = (sizeof(int) * cta_seg.size() + 255) & ~size_t(255);
+    const size_t b_tiles = (sizeof(TileInfo) * tiles.size() + 255) & ~size_t(255);
+    unsigned char* ws = nullptr;
+    MOR_TRY(scratch(b_part + b_segs + b_cta + b_tiles + 256, reinterpret_cast<void**>(&ws)));
+    double* part = reinterpret_cast<double*>(ws);
+    Seg* d_segs = reinterpret_cast<Seg*>(ws + ((b_part + 255) & ~size_t(255)));
+    int* d_cta = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(d_segs) + b_segs);
+    TileInfo* d_tiles = reinterpret_cast<TileInfo*>(reinterpret_cast<unsigned char*>(d_cta) + b_cta);
+    MOR_CUDA(cudaMemcpyAsync(d_segs, segs.data(), sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(d_cta, cta_seg.data(), sizeof(int) * cta_seg.size(), cudaMemcpyHostToDevice, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, cx.stream));
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOR_CUDA(cudaFuncSetAttribute(gemm_tn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
+        attr_set = true;
+    }
+    gemm_tn_sk_kernel<<<nct, 256, SK_SMEM, cx.stream>>>(maps, d_segs, d_cta, part);
+    MOR_CUDA(cudaGetLastError());
+    gemm_tn_sk_reduce_kernel<<<dim3(64, (unsigned)tiles.size()), 256, 0, cx.stream>>>(part, d_segs, d_tiles, same ? 1 : 0,
+                                                                                   p, q, C, ldc, accumulate);
+    MOR_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MOR_OK;
+}
+
+}  // namespace mor
