@@ -1,5 +1,7 @@
 // Context, error plumbing, device matrices, lifecycle entry points of libmor_b200.so.
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <mutex>
 
@@ -80,6 +82,26 @@ int32_t scratch(size_t bytes, void** out) {
     }
     *out = c.scratch_p;
     return MOR_OK;
+}
+
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+DebugLaps::DebugLaps(const char* what) : on(getenv("MOR_B200_DEBUG") != nullptr), t0(0.0) {
+    if (on) {
+        cudaStreamSynchronize(g_ctx.stream);
+        fprintf(stderr, "[mor_b200] %s\n", what);
+        t0 = now_ms();
+    }
+}
+void DebugLaps::lap(const char* label) {
+    if (!on) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    const double t = now_ms();
+    fprintf(stderr, "[mor_b200]   %-28s %9.3f ms\n", label, t - t0);
+    t0 = t;
 }
 
 Timer::Timer(int slot_) : slot(slot_) {}

@@ -226,14 +226,23 @@ __device__ __forceinline__ double warp_sum(double s) {
 
 // Replicated on every rank: choose the global winner, append its row to W = P'U (row i),
 // extend the LU factors (L row i, U-factor row i, Z column i) and compute the coefficient
-// vector c (length i+1) of the NEXT step.  All k x k arrays are row-major with stride k.
+// vector c (length i+1) of the NEXT step.  All k x k arrays are row-major with stride k; Zt is
+// the transpose of Z, kept so that every phase reads with the output index contiguous.
+// Every phase is a (triangular) matrix-vector product: thread (x, y) accumulates the terms
+// t = y (mod ways) of output x, the `ways` partial sums are combined through shared memory --
+// a sequential depth of k / ways instead of k on this latency-critical single-CTA kernel.
 __global__ void __launch_bounds__(1024)
 deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k, double* __restrict__ Wm,
                    double* __restrict__ Uf, double* __restrict__ Lm, double* __restrict__ Z,
-                   double* __restrict__ c, long long* __restrict__ idx_out, int* __restrict__ status) {
-    __shared__ double w[1024], ell[1024], ucol[1024], y[1024];
+                   double* __restrict__ Zt, double* __restrict__ c, long long* __restrict__ idx_out,
+                   int* __restrict__ status) {
+    __shared__ double w[1024], ell[1024], ucol[1024], y[1024], part[1024];
     __shared__ int win_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int KP = (k + 31) & ~31;       // outputs per phase, padded to whole warps
+    const int ways = 1024 / KP;          // reduction split (k <= 1024 => ways >= 1)
+    const int x = tid % KP, yy = tid / KP;
+    const bool active = yy < ways;
     const int stride = k + 2;
     if (tid == 0) {
         int win = 0;
@@ -259,41 +268,65 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
         Wm[(size_t)i * k + j] = v;
     }
     __syncthreads();
-    // L row: ell = w[0:i] * Z   (Z = inv(Uf[0:i,0:i]), upper triangular)
-    for (int j = tid; j < i; j += 1024) {
+    // combine the `ways` partial sums of output x (valid in threads with yy == 0)
+    auto combine = [&](double s) -> double {
+        part[tid] = s;
+        __syncthreads();
+        double tot = 0.0;
+        if (yy == 0)
+            for (int q = 0; q < ways; ++q) tot += part[q * KP + x];
+        __syncthreads();
+        return tot;
+    };
+    // L row: ell[j] = sum_{t <= j} w[t] * Z[t][j],  j < i   (Z = inv(Uf[0:i,0:i]), upper triangular)
+    {
         double s = 0.0;
-        for (int t = 0; t <= j; ++t) s = fma(w[t], Z[(size_t)t * k + j], s);
-        ell[j] = s;
-        Lm[(size_t)i * k + j] = s;
+        if (active && x < i)
+            for (int t = yy; t <= x; t += ways) s = fma(w[t], Z[(size_t)t * k + x], s);
+        s = combine(s);
+        if (yy == 0 && x < i) {
+            ell[x] = s;
+            Lm[(size_t)i * k + x] = s;
+        }
     }
     __syncthreads();
     // U-factor row i:  Uf[i][j] = w[j] - sum_{t<i} ell[t] * Uf[t][j],  j >= i
-    for (int j = i + tid; j < k; j += 1024) {
-        double s = w[j];
-        for (int t = 0; t < i; ++t) s = fma(-ell[t], Uf[(size_t)t * k + j], s);
-        Uf[(size_t)i * k + j] = s;
+    {
+        const int j = i + x;
+        double s = 0.0;
+        if (active && j < k)
+            for (int t = yy; t < i; t += ways) s = fma(ell[t], Uf[(size_t)t * k + j], s);
+        s = combine(s);
+        if (yy == 0 && j < k) Uf[(size_t)i * k + j] = w[j] - s;
     }
+    __syncthreads();
     for (int t = tid; t < i; t += 1024) ucol[t] = Uf[(size_t)t * k + i];
     __syncthreads();
     const double pivot = Uf[(size_t)i * k + i];
     if (tid == 0 && pivot == 0.0 && i < k - 1 && *status == 0) *status = i + 1;
-    // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot
-    for (int r = warp; r < i; r += 32) {
+    // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot,  r < i;  Z[i][i] = 1/pivot
+    {
         double s = 0.0;
-        for (int t = r + lane; t < i; t += 32) s = fma(Z[(size_t)r * k + t], ucol[t], s);
-        s = warp_sum(s);
-        if (lane == 0) Z[(size_t)r * k + i] = -s / pivot;
+        if (active && x < i)
+            for (int t = x + yy; t < i; t += ways) s = fma(Zt[(size_t)t * k + x], ucol[t], s);
+        s = combine(s);
+        if (yy == 0 && x <= i) {
+            const double z = (x == i) ? 1.0 / pivot : -s / pivot;
+            Z[(size_t)x * k + i] = z;
+            Zt[(size_t)i * k + x] = z;
+        }
     }
-    if (tid == 0) Z[(size_t)i * k + i] = 1.0 / pivot;
     if (i + 1 >= k) return;
+    __syncthreads();
     for (int t = tid; t <= i; t += 1024) y[t] = Uf[(size_t)t * k + i + 1];
     __syncthreads();
     // c = Z[0:i+1, 0:i+1] * y   (y = inv(L) * P'u_{l+1} is column i+1 of the U-factor)
-    for (int r = warp; r <= i; r += 32) {
+    {
         double s = 0.0;
-        for (int t = r + lane; t <= i; t += 32) s = fma(Z[(size_t)r * k + t], y[t], s);
-        s = warp_sum(s);
-        if (lane == 0) c[r] = s;
+        if (active && x <= i)
+            for (int t = x + yy; t <= i; t += ways) s = fma(Zt[(size_t)t * k + x], y[t], s);
+        s = combine(s);
+        if (yy == 0 && x <= i) c[x] = s;
     }
 }
 
@@ -322,8 +355,8 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
 
     const size_t kk = (size_t)k * k;
     DevBuf state, cands, xfer;
-    // state: Wm, Uf, Lm, Z (k*k each), c (k), idx (k int64), status
-    MOR_TRY(state.alloc(sizeof(double) * (4 * kk + k) + sizeof(long long) * k + 16));
+    // state: Wm, Uf, Lm, Z, Zt (k*k each), c (k), idx (k int64), status
+    MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k) + sizeof(long long) * k + 16));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
     MOR_TRY(xfer.alloc(sizeof(double) * (size_t)(k + 2) * (size_t)(cx.nranks + 1)));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
@@ -331,7 +364,8 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* Uf = Wm + kk;
     double* Lm = Uf + kk;
     double* Z = Lm + kk;
-    double* c = Z + kk;
+    double* Zt = Z + kk;
+    double* c = Zt + kk;
     long long* idx_d = reinterpret_cast<long long*>(c + k);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
     double* send = xfer.as<double>();
@@ -349,7 +383,7 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         t_tail.start();
         deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send);
         if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)(k + 2)));
-        deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, i, (int)k, Wm, Uf, Lm, Z, c, idx_d, status_d);
+        deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, i, (int)k, Wm, Uf, Lm, Z, Zt, c, idx_d, status_d);
         t_tail.stop();
         count_launch(3);
     }

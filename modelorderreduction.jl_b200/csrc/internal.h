@@ -54,6 +54,15 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 // scratch() call on this context (all users are ordered on ctx().stream).
 int32_t scratch(size_t bytes, void** out);
 
+// Debug stopwatch: when MOR_B200_DEBUG is set, lap("label") synchronises the stream and prints the
+// wall time since the previous lap to stderr (serialises the pipeline: for diagnosis only).
+struct DebugLaps {
+    bool on;
+    double t0;
+    explicit DebugLaps(const char* what);
+    void lap(const char* label);
+};
+
 // RAII device buffer (freed with cudaFree on destruction)
 struct DevBuf {
     void* p = nullptr;

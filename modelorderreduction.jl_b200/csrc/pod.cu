@@ -143,14 +143,17 @@ int32_t gram_pass(const double* T, int64_t trows, int n, int64_t ldt, bool repli
         tm.comm.stop();
     }
     tm.core.start();
+    DebugLaps dbg("gram_pass: scaled Cholesky");
     double shift = 0.0;
     SmallInfo h;
     for (int attempt = 0;; ++attempt) {
         MOR_TRY(small_info_reset(d_info));
         MOR_TRY(small_diag(G, n, n, D, d_info));
         MOR_TRY(small_scale(G, n, n, D, shift, Rs, n, d_info));
+        dbg.lap("diag + scale");
         MOR_TRY(small_chol_upper(Rs, n, n, d_info));
         MOR_TRY(small_info_read(d_info, &h));
+        dbg.lap("blocked Cholesky");
         if (h.nonfinite) {
             tm.core.stop();
             set_error("POD: the snapshot matrix contains Inf or NaN");
@@ -280,6 +283,7 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     // only an optional output there).  For a wide input the small-side vectors ARE the basis, so
     // V is accumulated and stays orthonormal to rounding for every column.
     tm.core.start();
+    DebugLaps dbg("factor_tall: core SVD");
     const bool accumulate_v = replicated || n < 64;
     MOR_TRY(A.alloc(nn));
     MOR_CUDA(cudaMemcpyAsync(A.p, Rtot.p, nn, cudaMemcpyDeviceToDevice, st));
@@ -288,11 +292,13 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     if (!accumulate_v) MOR_CUDA(cudaMemcpyAsync(Rtot.p, A.p, nn, cudaMemcpyDeviceToDevice, st));  // keep R (deflated)
     std::vector<int> order;
     int sweeps = 0;
+    dbg.lap("copy R / deflate");
     int32_t js = jacobi_svd(A.as<double>(), n, n, n, accumulate_v ? V.as<double>() : nullptr, n, h->sigma, order, &sweeps);
     if (js != MOR_OK) {
         tm.core.stop();
         return js;
     }
+    dbg.lap("jacobi_svd");
     DevBuf perm, inv_sigma, inv_vn, inv_both;
     MOR_TRY(upload_perm(order, perm));
     std::vector<double> is((size_t)n), iv((size_t)n, 1.0), ib((size_t)n);
@@ -329,6 +335,7 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
             MOR_TRY(small_scale_rc(h->Vs.as<double>(), n, n, n, inv_sigma.as<double>(), /*rows=*/false, /*inv=*/false));
         }
     }
+    dbg.lap("basis maker M, right vectors");
     MOR_TRY(sign_fix(h->Vs.as<double>(), n, n, n, h->M.as<double>(), n, n));
     MOR_CUDA(cudaStreamSynchronize(st));  // perm / inv_sigma are released on return
     tm.core.stop();
