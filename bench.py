@@ -273,20 +273,42 @@ def run_ours(args):
     parts = {s: acc[s] / args.steps for s in slots if s != "total"}
     value = pod_flops(M, n, k) / (pod_ms * 1e-3) * 1e-12
 
-    # ---- validity checks outside the timed region ---------------------------------------------
+    # ---- validity checks outside the timed region: size-independent properties at FULL size ----
+    # (no CPU oracle fits 16M rows): U_k orthonormal; (sigma_i, u_i, v_i) are singular triplets of X
+    # (X'U_k = V_k S_k); the full spectrum carries all the energy (sum sigma^2 = ||X||_F^2, the norm
+    # computed independently by torch on the same device memory).
     lib.mor_dbg_gemm_tn.restype = C.c_int32
-    UtU = DeviceMatrix.alloc(k, k)
+    f = pod_factor_dev(X, _lib.MOR_SVD, k, m_global=M)
+    f.basis(k, U)
+    s = f.s
+    Vk = f.right(k, DeviceMatrix.alloc(n, k)).to_host()
+    UtU, XtU = DeviceMatrix.alloc(k, k), DeviceMatrix.alloc(n, k)
     _lib.check(lib.mor_dbg_gemm_tn(U.handle, U.handle, UtU.handle))
+    _lib.check(lib.mor_dbg_gemm_tn(X.handle, U.handle, XtU.handle))
     g = torch.from_numpy(np.ascontiguousarray(UtU.to_host())).cuda()
+    w = torch.from_numpy(np.ascontiguousarray(XtU.to_host())).cuda()
+
+    class _Alias:  # torch view of the library-owned column-major X: (n, ld) row-major
+        def __init__(self, ptr, rows, ld):
+            self.__cuda_array_interface__ = {"shape": (rows, ld), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    xm, xn, xld, xptr = X.info
+    xt = torch.as_tensor(_Alias(xptr, xn, xld), device="cuda")
+    fro2 = torch.zeros((), dtype=torch.float64, device="cuda")
+    for j0 in range(0, xn, 64):
+        fro2 += torch.linalg.vector_norm(xt[j0:j0 + 64, :xm]) ** 2
     if world > 1:
         dist.all_reduce(g)
+        dist.all_reduce(w)
+        dist.all_reduce(fro2)
     orth_err = float((g - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item())
-    s = info["s"]
+    resid = float((w - torch.from_numpy(Vk * s[:k]).cuda()).abs().max().item() / s[0])
+    energy_err = float(abs(np.sum(s * s) / float(fro2.item()) - 1.0))
     d = 10.0 ** (-3.0 * np.arange(n) / (n - 1))
     sig_dev = float(np.max(np.abs(s / (math.sqrt(M) * d) - 1.0)))   # sigma_j ~ sqrt(m) d_j up to O(sqrt(n/m))
-    checks = {"basis_orthonormality_max_abs": orth_err, "sigma_vs_sqrt_m_times_scale_max_rel": sig_dev,
-              "cholqr_passes": info["passes"], "jacobi_sweeps": info["sweeps"]}
-    UtU.free()
+    checks = {"basis_orthonormality_max_abs": orth_err, "triplet_residual_max_abs_over_sigma1": resid,
+              "energy_identity_rel_err": energy_err, "sigma_vs_sqrt_m_times_scale_max_rel": sig_dev,
+              "sigma_head": [float(v) for v in s[:4]], "cholqr_passes": info["passes"], "jacobi_sweeps": info["sweeps"]}
+    f.free(); UtU.free(); XtU.free(); del xt
 
     # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region ----------
     e2e = None
@@ -327,6 +349,38 @@ def run_ours(args):
             lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
     X.free(); U.free()
 
+    # ---- RSVD (BASELINE config 4 at N = 8: 64M x 512, k = 64, p = 0): 8M rows per GPU ----------------
+    rsvd = None
+    if not args.no_rsvd:
+        Mr, nr, kr = args.rsvd_rows_per_gpu * world, 512, 64
+        r0r, mr_loc = mdist.shard_rows(Mr, world, rank)
+        Xr = DeviceMatrix.alloc(mr_loc, nr).synth(_lib.SYNTH_LOWRANK, seed=4, global_row0=r0r, param=3.0, iparam=64)
+        Om = DeviceMatrix.alloc(nr, kr).synth(_lib.SYNTH_GAUSS, seed=40, global_row0=0, param=1.0)
+        Ur = DeviceMatrix.alloc(mr_loc, kr)
+
+        def rsvd_step():
+            fr = pod_factor_dev(Xr, _lib.MOR_RSVD, kr, p=0, omega=Om, m_global=Mr)
+            t = _lib.last_timings()
+            fr.basis(kr, Ur)
+            passes = fr.info()[0]
+            fr.free()
+            return t, passes
+        for _ in range(2):
+            rsvd_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(3):
+            tr, rpasses = rsvd_step()
+        e1.record(stream)
+        barrier()
+        rsvd_ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+        fl = 4.0 * Mr * nr * kr + 2.0 * Mr * kr * kr + 2.0 * Mr * kr * kr
+        rsvd = {"workload": f"RSVD(0) of a synthetic {Mr}x{nr} FP64 matrix (rank-64 dominant part), k=64, Philox Omega "
+                            f"seed 40, {mr_loc} rows per GPU", "ms": rsvd_ms, "algorithmic_tflops": fl / (rsvd_ms * 1e-3) * 1e-12,
+                "algorithmic_gbs": 16.0 * Mr * nr / (rsvd_ms * 1e-3) * 1e-9, "orth_passes": rpasses,
+                "breakdown_ms": {k_: tr[k_] for k_ in ("sketch", "gram", "apply", "core", "comm")}}
+        Xr.free(); Om.free(); Ur.free()
+
     # ---- DEIM: 16M x 256 orthonormal basis, row-sharded ------------------------------------------
     Md, kd = args.deim_rows, DEIM_K
     r0d, md_loc = mdist.shard_rows(Md, world, rank)
@@ -346,6 +400,25 @@ def run_ours(args):
     barrier()
     deim_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     deim_step_ms = max_over_ranks(dacc["deim_step"] / args.steps)
+    # DEIM through the host-pointer entry point (what the Julia shim calls), pinned host basis
+    deim_e2e = None
+    if not args.no_e2e and md_loc * kd * 8 / 1e9 * 1.15 + 8 < mem_available_gb() / max(1, min(world, 8)):
+        Bh = C.c_void_p()
+        _lib.check(lib.mor_b200_host_alloc(md_loc * kd * 8, C.byref(Bh)))
+        _lib.check(lib.mor_b200_mat_download(B.handle, Bh, max(md_loc, 1)))
+        idx_h = np.empty(kd, dtype=np.int64)
+        for it in range(args.e2e_warmup + args.e2e_steps):
+            if it == args.e2e_warmup:
+                barrier()
+                t0 = time.perf_counter()
+            _lib.check(lib.mor_b200_deim_indices(Bh, md_loc, kd, max(md_loc, 1), idx_h.ctypes.data))
+        barrier()
+        deim_e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps * 1e3)
+        deim_e2e = {"ms": deim_e2e_ms, "algorithmic_gbs": deim_bytes(Md, kd) / (deim_e2e_ms * 1e-3) * 1e-9,
+                    "h2d_bytes_per_step": int(sum_over_ranks(md_loc * kd * 8)), "d2h_bytes_per_step": kd * 8,
+                    "same_indices_as_device_path": bool(np.array_equal(idx_h, idx)),
+                    "api": "mor_b200_deim_indices (host pointers, pinned)"}
+        lib.mor_b200_host_free(Bh)
     deim_gbs = deim_bytes(Md, kd) / (deim_ms * 1e-3) * 1e-9
     deim = {"ms": deim_ms, "algorithmic_gbs": deim_gbs, "m": Md, "k": kd, "distinct_indices": len(set(idx.tolist())),
             "basis": f"Philox Gaussian orthonormalised by the library's CholeskyQR ({orth_passes} passes)",
@@ -354,7 +427,7 @@ def run_ours(args):
                          "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                          "frac": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9 / hbm_peak,
                          "live_read_peak_gbs": pk_g.value, "traffic": None},
-            "tail_ms": dacc["deim_tail"] / args.steps}
+            "tail_ms": dacc["deim_tail"] / args.steps, "e2e": deim_e2e}
     B.free()
     if world > 1:
         dist.barrier()
@@ -385,7 +458,7 @@ def run_ours(args):
                                         "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
                          "frac": achieved / pk_t.value if pk_t.value else None, "traffic": None,
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
-            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "cpu_baseline": cpu}
+            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 
@@ -402,6 +475,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rsvd", action="store_true")
+    ap.add_argument("--rsvd-rows-per-gpu", type=int, default=8 * 2**20)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

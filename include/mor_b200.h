@@ -113,6 +113,22 @@ int32_t mor_b200_pod_info(mor_pod_t handle, int32_t* passes, int32_t* sweeps);
  * counts as maximal (Julia argmax). */
 int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out);
 
+/* DEIM projector, deim.jl:150: P = ((U[idx, :])' \ (U' * V))'  (pod_dim x deim_dim, ld = ldp),
+ * U (m x kd) the DEIM basis, V (m x kp) the POD basis (this rank's row shards), idx the kd global
+ * 1-based interpolation indices.  P is replicated on every rank. */
+int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp,
+                                int64_t ldv, const int64_t* idx, double* P_out, int64_t ldp);
+
+/* Galerkin projection of the linear part, deim.jl:154-155,261.
+ * A_hat (k x k, ld = lda) = V' * A * V with A an m x m Julia SparseMatrixCSC given by its own arrays
+ * (colptr m+1 entries, rowval / nzval nnz entries, 1-based Int64 indices); single rank. */
+int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                              const double* V, int64_t k, int64_t ldv, double* Ahat, int64_t lda);
+/* out (k x nvec, ld = ldo) = V' * Xv: g_hat = V' * g and y_hat(0) = V' * snapshot[:, 1].  V (m x k) and
+ * Xv (m x nvec) are this rank's row shards; the result is replicated. */
+int32_t mor_b200_project(const double* V, int64_t m, int64_t k, int64_t ldv, const double* Xv, int64_t nvec,
+                         int64_t ldx, double* out, int64_t ldo);
+
 /* ---- device-resident API (inputs already in HBM; used by bench and GPU-side callers) --- */
 int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out);
 /* Borrow caller-owned device memory (e.g. a torch tensor); never freed by the library. */
@@ -133,10 +149,13 @@ int32_t mor_b200_pod_factor_dev(mor_mat_t X, int32_t method, int64_t k, int64_t 
                                 int64_t* nS);
 /* U (m x k) is written into the device matrix U_out (allocated by the caller, m x >=k). */
 int32_t mor_b200_pod_basis_dev(mor_pod_t handle, int64_t k, mor_mat_t U_out);
+/* Leading k right singular vectors (n x k, replicated on every rank) into the device matrix V_out. */
+int32_t mor_b200_pod_right_dev(mor_pod_t handle, int64_t k, mor_mat_t V_out);
 /* Orthonormalise the columns of A in place (CholeskyQR passes until ||A'A - I|| is at
  * rounding level); used to build the DEIM benchmark basis. */
 int32_t mor_b200_orthonormalize_dev(mor_mat_t A, int32_t* passes);
 int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out);
+int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx, mor_mat_t P_out);
 
 /* ---- instrumentation ----------------------------------------------------------------------
  * CUDA-event timings (ms) of the last POD/DEIM call on this rank, by slot: */

@@ -39,13 +39,29 @@ int32_t require_ctx() {
 // Small work buffers come from the stream-ordered pool (cudaMallocAsync): a plain
 // cudaMalloc/cudaFree pair costs ~25 ms each next to a 100+ GB allocation (measured: 300 ms of
 // a 980 ms POD step), the pool costs microseconds and never synchronises the device.
-static constexpr size_t POOL_LIMIT = size_t(256) << 20;
+static constexpr size_t POOL_LIMIT = size_t(8) << 30;   // larger buffers (snapshot copies) use cudaMalloc
+static constexpr uint64_t POOL_KEEP = uint64_t(8) << 30;  // freed work memory the pool may keep cached
+
+// give cached pool memory back to the driver (used before retrying a failed cudaMalloc)
+static void trim_pool() {
+    cudaMemPool_t pool = nullptr;
+    if (g_ctx.ready && cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) {
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+}
 
 int32_t DevBuf::alloc(size_t nbytes) {
     release();
     if (nbytes == 0) nbytes = 8;
     pooled = nbytes <= POOL_LIMIT && g_ctx.ready;
     cudaError_t e = pooled ? cudaMallocAsync(&p, nbytes, g_ctx.stream) : cudaMalloc(&p, nbytes);
+    if (e == cudaErrorMemoryAllocation) {  // the pool may be sitting on the memory we need
+        cudaGetLastError();
+        trim_pool();
+        e = pooled ? cudaMallocAsync(&p, nbytes, g_ctx.stream) : cudaMalloc(&p, nbytes);
+    }
     if (e != cudaSuccess) {
         p = nullptr;
         return cuda_fail(e, pooled ? "cudaMallocAsync" : "cudaMalloc", __FILE__, __LINE__);
@@ -74,6 +90,11 @@ int32_t scratch(size_t bytes, void** out) {
         }
         size_t want = bytes + bytes / 4;
         cudaError_t e = cudaMalloc(&c.scratch_p, want);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            trim_pool();
+            e = cudaMalloc(&c.scratch_p, want);
+        }
         if (e != cudaSuccess) {
             c.scratch_p = nullptr;
             return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
@@ -170,10 +191,10 @@ int32_t mor_b200_init(int32_t device) {
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
     MOR_CUDA(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
     g_ctx.stream = g_ctx.own_stream;
-    {   // keep up to 2 GB of freed work buffers cached in the default pool
+    {   // keep up to POOL_KEEP of freed work buffers cached in the default pool
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = uint64_t(2) << 30;
+            uint64_t keep = POOL_KEEP;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         cudaGetLastError();
@@ -255,6 +276,11 @@ int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
     size_t bytes = (size_t)ld * (size_t)(n > 0 ? n : 1) * sizeof(double);
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        trim_pool();
+        e = cudaMalloc(&p, bytes);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(matrix)", __FILE__, __LINE__);
     if (ld != m) {  // keep the pad row finite
         MOR_CUDA(cudaMemsetAsync(p, 0, bytes, g_ctx.stream));

@@ -406,11 +406,82 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     return MOR_OK;
 }
 
+// DEIM projector of the reduced nonlinear term, reference src/deim.jl:150:
+//     projector = ((@view U[indices, :])' \ (U' * V))'        (pod_dim x deim_dim)
+// U'V is a tall-skinny contraction over the row shards (gemm_tn + all-reduce), U[indices, :] is
+// gathered from whichever rank owns each selected row, the kd x kd solve is LU with partial
+// pivoting (Julia's `\` for a general square matrix), replicated on every rank.
+int32_t deim_projector_device(const double* U, int64_t m, int kd, int64_t ldu, const double* V, int kp, int64_t ldv,
+                              const int64_t* idx_host, double* P_dev, int64_t ldp) {
+    Ctx& cx = ctx();
+    MOR_ARG(U && V && idx_host && P_dev, "deim_projector: null pointer");
+    MOR_ARG(kd >= 1 && kd <= 1024 && kp >= 1 && kp <= 4096 && ldp >= kp, "deim_projector: bad dimensions");
+    std::vector<int64_t> all_m;
+    MOR_TRY(comm_allgather_i64(m, all_m));
+    int64_t row_offset = 0, m_global = 0;
+    for (int r = 0; r < cx.nranks; ++r) {
+        if (r < cx.rank) row_offset += all_m[r];
+        m_global += all_m[r];
+    }
+    for (int i = 0; i < kd; ++i)
+        MOR_ARG(idx_host[i] >= 1 && idx_host[i] <= m_global, "deim_projector: interpolation index out of range");
+    DevBuf UtV, PtU, d_idx, d_fail;
+    MOR_TRY(UtV.alloc(sizeof(double) * (size_t)kd * kp));
+    MOR_TRY(PtU.alloc(sizeof(double) * (size_t)kd * kd));
+    MOR_TRY(d_idx.alloc(sizeof(long long) * (size_t)kd));
+    MOR_TRY(d_fail.alloc(sizeof(int)));
+    std::vector<long long> idx_ll(idx_host, idx_host + kd);
+    MOR_CUDA(cudaMemcpyAsync(d_idx.p, idx_ll.data(), sizeof(long long) * (size_t)kd, cudaMemcpyHostToDevice, cx.stream));
+    MOR_TRY(gemm_tn(U, ldu, kd, V, ldv, kp, m, UtV.as<double>(), kd));
+    MOR_TRY(gather_rows(U, m, ldu, row_offset, d_idx.as<long long>(), kd, PtU.as<double>(), kd));
+    if (cx.nranks > 1) {
+        MOR_TRY(comm_allreduce_sum(UtV.as<double>(), (size_t)kd * kp));
+        MOR_TRY(comm_allreduce_sum(PtU.as<double>(), (size_t)kd * kd));
+    }
+    MOR_TRY(small_lu_solve(PtU.as<double>(), kd, kd, /*transpose=*/true, UtV.as<double>(), kp, kd, d_fail.as<int>()));
+    MOR_TRY(transpose(UtV.as<double>(), kd, kp, kd, P_dev, ldp));
+    int fail = 0;
+    MOR_CUDA(cudaMemcpyAsync(&fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaStreamSynchronize(cx.stream));
+    if (fail != 0) {
+        set_error("deim_projector: U[indices, :] is exactly singular (SingularException in the reference)");
+        return MOR_ERR_SINGULAR;
+    }
+    return MOR_OK;
+}
+
 }  // namespace mor
 
 using namespace mor;
 
 extern "C" {
+
+int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx, mor_mat_t P_out) {
+    MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector_dev: null argument");
+    MOR_ARG(U->m == V->m && P_out->m == V->n && P_out->n == U->n, "mor_b200_deim_projector_dev: P_out must be pod_dim x deim_dim");
+    MOR_TRY(require_ctx());
+    return deim_projector_device(U->p, U->m, (int)U->n, U->ld, V->p, (int)V->n, V->ld, idx, P_out->p, P_out->ld);
+}
+
+int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp,
+                                int64_t ldv, const int64_t* idx, double* P_out, int64_t ldp) {
+    MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector: null pointer");
+    MOR_ARG(m >= 0 && kd >= 1 && kp >= 1 && ldu >= (m > 0 ? m : 1) && ldv >= (m > 0 ? m : 1) && ldp >= kp,
+            "mor_b200_deim_projector: bad dimensions");
+    MOR_TRY(require_ctx());
+    mor_mat_t dU = nullptr, dV = nullptr, dP = nullptr;
+    int32_t st = mor_b200_mat_alloc(m, kd, &dU);
+    if (st == MOR_OK) st = mor_b200_mat_alloc(m, kp, &dV);
+    if (st == MOR_OK) st = mor_b200_mat_alloc(kp, kd, &dP);
+    if (st == MOR_OK) st = mor_b200_mat_upload(dU, U, ldu);
+    if (st == MOR_OK) st = mor_b200_mat_upload(dV, V, ldv);
+    if (st == MOR_OK) st = mor_b200_deim_projector_dev(dU, dV, idx, dP);
+    if (st == MOR_OK) st = mor_b200_mat_download(dP, P_out, ldp);
+    mor_b200_mat_free(dU);
+    mor_b200_mat_free(dV);
+    mor_b200_mat_free(dP);
+    return st;
+}
 
 int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {
     MOR_ARG(B != nullptr, "mor_b200_deim_indices_dev: null matrix");

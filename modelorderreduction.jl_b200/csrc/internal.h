@@ -151,6 +151,11 @@ int32_t small_gemm(bool ta, bool tb, int m, int n, int k, double alpha, const do
 // A[i][j] *= s with s = d[i] (rows) or d[j]; inv: s = 1/d; a zero entry of d acts as 1
 int32_t small_scale_rc(double* A, int m, int n, int ld, const double* d, bool rows, bool inv);
 int32_t small_identity(double* A, int n, int ld);
+// A X = B (or A' X = B) by LU with partial pivoting, in place; *d_fail (device int) = 1-based zero pivot
+int32_t small_lu_solve(double* A, int n, int lda, bool transpose, double* B, int nrhs, int ldb, int* d_fail);
+// out (k x k) = rows idx[i]-1 (global, 1-based) of this rank's shard of U (m x k), zeros for rows of other ranks
+int32_t gather_rows(const double* U, int64_t m, int64_t ld, int64_t row0, const long long* d_idx, int k, double* out,
+                    int ldo);
 int32_t small_zero_rows(double* A, int m, int n, int ld, const double* flag);
 int32_t transpose(const double* in, int64_t rows, int64_t cols, int64_t ldin, double* out, int64_t ldout);
 int32_t gather_cols(const double* in, int ldin, int rows, int ncols, const int* d_perm, const double* d_scale,

@@ -652,6 +652,26 @@ int32_t mor_b200_pod_basis_dev(mor_pod_t h, int64_t k, mor_mat_t U_out) {
     return st;
 }
 
+int32_t mor_b200_pod_right_dev(mor_pod_t h, int64_t k, mor_mat_t V_out) {
+    MOR_ARG(h != nullptr && V_out != nullptr, "mor_b200_pod_right_dev: null argument");
+    MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_right_dev: k must be in 1..number of computed triplets");
+    MOR_ARG(V_out->m == h->n && V_out->n >= k, "mor_b200_pod_right_dev: V_out must be n x >= k");
+    MOR_TRY(require_ctx());
+    reset_timings();
+    Timers tm;
+    int32_t st = MOR_OK;
+    if (h->wide) {  // the right vectors of a wide X are the tall side of its transpose
+        st = tall_vectors(h, (int)k, V_out->p, V_out->ld, tm);
+    } else {
+        cudaError_t e = cudaMemcpy2DAsync(V_out->p, (size_t)V_out->ld * 8, h->Vs.p, (size_t)h->vs_rows * 8,
+                                          (size_t)h->vs_rows * 8, (size_t)k, cudaMemcpyDeviceToDevice, ctx().stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMemcpy2DAsync", __FILE__, __LINE__);
+    }
+    cudaStreamSynchronize(ctx().stream);
+    tm.collect();
+    return st;
+}
+
 int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, double* V_out, int64_t ldv) {
     MOR_ARG(h != nullptr && U_out != nullptr, "mor_b200_pod_basis: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_basis: k must be in 1..number of computed triplets");

@@ -269,7 +269,118 @@ __global__ void transpose_kernel(const double* __restrict__ in, long long rows, 
     }
 }
 
+// Solve A X = B by LU with partial pivoting (what Julia's `\` does for a general square matrix:
+// dgetrf + dgetrs), one CTA, A (n x n) and B (n x nrhs) column-major in L2, both overwritten.
+// transpose != 0 solves A' X = B instead (A is read transposed).  *fail = 1-based zero pivot.
+__global__ void __launch_bounds__(1024)
+lu_solve_kernel(double* __restrict__ A, int n, int lda, int transpose, double* __restrict__ B, int nrhs, int ldb,
+                int* __restrict__ fail) {
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    __shared__ int piv_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto at = [&](int r, int c) -> double& { return transpose ? A[(size_t)r * lda + c] : A[(size_t)c * lda + r]; };
+    for (int j = 0; j < n; ++j) {
+        // pivot: first row of maximal |A[r][j]|, r >= j (idamax semantics)
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int r = j + tid; r < n; r += 1024) {
+            const double v = fabs(at(r, j));
+            if (v > bv) {
+                bv = v;
+                bi = r;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            sv[warp] = bv;
+            si[warp] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; ++w)
+                if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) {
+                    bv = sv[w];
+                    bi = si[w];
+                }
+            piv_s = bi;
+            if (!(bv > 0.0) && *fail == 0) *fail = j + 1;
+        }
+        __syncthreads();
+        const int pv = piv_s;
+        if (pv != j && pv < n) {
+            for (int c = tid; c < n; c += 1024) {
+                const double t = at(j, c);
+                at(j, c) = at(pv, c);
+                at(pv, c) = t;
+            }
+            for (int c = tid; c < nrhs; c += 1024) {
+                const double t = B[(size_t)c * ldb + j];
+                B[(size_t)c * ldb + j] = B[(size_t)c * ldb + pv];
+                B[(size_t)c * ldb + pv] = t;
+            }
+        }
+        __syncthreads();
+        const double d = at(j, j);
+        for (int r = j + 1 + tid; r < n; r += 1024) at(r, j) = at(r, j) / d;
+        __syncthreads();
+        const int rem = n - j - 1;
+        for (int e = tid; e < rem * rem; e += 1024) {
+            const int r = j + 1 + e % rem, c = j + 1 + e / rem;
+            at(r, c) = fma(-at(r, j), at(j, c), at(r, c));
+        }
+        for (int e = tid; e < rem * nrhs; e += 1024) {
+            const int r = j + 1 + e % rem, c = e / rem;
+            B[(size_t)c * ldb + r] = fma(-at(r, j), B[(size_t)c * ldb + j], B[(size_t)c * ldb + r]);
+        }
+        __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        const double d = at(j, j);
+        for (int c = tid; c < nrhs; c += 1024) B[(size_t)c * ldb + j] /= d;
+        __syncthreads();
+        for (int e = tid; e < j * nrhs; e += 1024) {
+            const int r = e % j, c = e / j;
+            B[(size_t)c * ldb + r] = fma(-at(r, j), B[(size_t)c * ldb + j], B[(size_t)c * ldb + r]);
+        }
+        __syncthreads();
+    }
+}
+
+// out[i][j] = (row0 <= idx[i]-1 < row0 + m) ? U[idx[i]-1-row0][j] : 0   (k x k gather of the selected rows)
+__global__ void gather_rows_kernel(const double* __restrict__ U, long long m, long long ld, long long row0,
+                                   const long long* __restrict__ idx, int k, double* __restrict__ out, int ldo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= k) return;
+    const long long r = idx[i] - 1 - row0;
+    out[(size_t)j * ldo + i] = (r >= 0 && r < m) ? U[(size_t)j * ld + r] : 0.0;
+}
+
 }  // namespace
+
+int32_t small_lu_solve(double* A, int n, int lda, bool transpose, double* B, int nrhs, int ldb, int* d_fail) {
+    MOR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), ctx().stream));
+    lu_solve_kernel<<<1, 1024, 0, ctx().stream>>>(A, n, lda, transpose ? 1 : 0, B, nrhs, ldb, d_fail);
+    count_launch();
+    MOR_CUDA(cudaGetLastError());
+    return MOR_OK;
+}
+
+int32_t gather_rows(const double* U, int64_t m, int64_t ld, int64_t row0, const long long* d_idx, int k, double* out,
+                    int ldo) {
+    gather_rows_kernel<<<dim3((k + 127) / 128, k), 128, 0, ctx().stream>>>(U, m, ld, row0, d_idx, k, out, ldo);
+    count_launch();
+    MOR_CUDA(cudaGetLastError());
+    return MOR_OK;
+}
 
 int32_t small_info_reset(SmallInfo* d_info) {
     MOR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(SmallInfo), ctx().stream));

@@ -161,4 +161,20 @@ function deim_interpolation_indices(B::F64Mat)::Vector{Int}
     return idx
 end
 
+# deim.jl:150 -- `projector = ((@view U[indices, :])' \ (U' * V))'`.  The expression sits inside the
+# numeric `deim(...)` method, so it cannot be rerouted by dispatch; a maintainer replaces that one
+# line by `projector = MORB200.deim_projector(U, V, indices)` (see INTEGRATION.md).
+function deim_projector(U::F64Mat, V::F64Mat, indices::Vector{Int})
+    stride(U, 1) == 1 || (U = Matrix(U))
+    stride(V, 1) == 1 || (V = Matrix(V))
+    n, kd = size(U)
+    kp = size(V, 2)
+    P = Matrix{Float64}(undef, kp, kd)
+    idx = Vector{Int64}(indices)
+    GC.@preserve U V idx check(ccall((:mor_b200_deim_projector, LIB), Cint,
+        (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Int64),
+        U, n, kd, max(stride(U, 2), 1), V, kp, max(stride(V, 2), 1), idx, P, max(kp, 1)))
+    return P
+end
+
 end # module

@@ -59,6 +59,10 @@ SIGNATURES = {
     "mor_b200_pod_free": (_i32, [_p]),
     "mor_b200_pod_info": (_i32, [_p, _pi32, _pi32]),
     "mor_b200_deim_indices": (_i32, [_p, _i64, _i64, _i64, _p]),
+    "mor_b200_deim_projector": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _p, _i64]),
+    "mor_b200_deim_projector_dev": (_i32, [_p, _p, _p, _p]),
+    "mor_b200_galerkin_csc": (_i32, [_i64, _p, _p, _p, _p, _i64, _i64, _p, _i64]),
+    "mor_b200_project": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64]),
     "mor_b200_mat_alloc": (_i32, [_i64, _i64, C.POINTER(_p)]),
     "mor_b200_mat_wrap": (_i32, [_p, _i64, _i64, _i64, C.POINTER(_p)]),
     "mor_b200_mat_free": (_i32, [_p]),
@@ -69,6 +73,7 @@ SIGNATURES = {
     "mor_b200_pod_factor_dev": (_i32, [_p, _i32, _i64, _i64, _p, _u64, _i32, C.POINTER(_p), _p,
                                        _pi64]),
     "mor_b200_pod_basis_dev": (_i32, [_p, _i64, _p]),
+    "mor_b200_pod_right_dev": (_i32, [_p, _i64, _p]),
     "mor_b200_orthonormalize_dev": (_i32, [_p, _pi32]),
     "mor_b200_deim_indices_dev": (_i32, [_p, _p]),
     "mor_b200_last_timings": (_i32, [_pd, _i32]),

@@ -82,6 +82,10 @@ class DeviceFactor:
         _lib.check(_lib.load().mor_b200_pod_basis_dev(self.handle, k, out.handle))
         return out
 
+    def right(self, k: int, out: DeviceMatrix) -> DeviceMatrix:
+        _lib.check(_lib.load().mor_b200_pod_right_dev(self.handle, k, out.handle))
+        return out
+
     def info(self):
         passes, sweeps = C.c_int32(0), C.c_int32(0)
         _lib.check(_lib.load().mor_b200_pod_info(self.handle, C.byref(passes), C.byref(sweeps)))

@@ -254,6 +254,13 @@ def deim_interpolation_indices(basis: Array) -> Array:
     return indices + 1
 
 
+def deim_projector(U: Array, V: Array, indices: Array) -> Array:
+    """deim.jl:150 -- ``projector = ((@view U[indices, :])' \\ (U' * V))'``: generic square backslash
+    (LU with partial pivoting = dgetrf/dgetrs) on the transposed selected rows."""
+    PtU = np.asarray(U)[np.asarray(indices) - 1, :]
+    return np.linalg.solve(PtU.T, np.asarray(U).T @ np.asarray(V)).T
+
+
 # --------------------------------------------------------------------------------------
 # Row-sharded restatements (the exchange steps of SURVEY.md section 8e), used to check
 # that the multi-GPU algorithm -- not just its kernels -- reproduces the reference.

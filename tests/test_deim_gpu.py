@@ -87,3 +87,55 @@ def test_device_resident_and_properties(gpu):
     assert idx.tolist() == O.deim_interpolation_indices(host).tolist()
     t = _lib.last_timings()
     assert t["deim_step"] > 0 and t["total"] >= t["deim_step"]
+
+
+def test_deim_projector_vs_oracle(gpu):
+    """deim.jl:150: projector = ((U[idx,:])' \\ (U'V))' -- next row of the hot path."""
+    import fhn_fixture as F
+    rng = np.random.Generator(np.random.PCG64(77))
+    for (n, kd, kp) in [(40, 3, 5), (5000, 24, 10), (120_001, 64, 64), (30_000, 130, 70)]:
+        U, _ = np.linalg.qr(rng.standard_normal((n, kd)))
+        V, _ = np.linalg.qr(rng.standard_normal((n, kp)))
+        idx = O.deim_interpolation_indices(U)
+        P = mor_b200.deim_projector(U, V, idx)
+        Pref = O.deim_projector(U, V, idx)
+        assert P.shape == (kp, kd)
+        assert np.max(np.abs(P - Pref)) <= 1e-10 * np.max(np.abs(Pref))
+    # the README example end to end: POD5 / DEIM5 of FitzHugh-Nagumo, the v-block of the state basis
+    X = F.snapshots()
+    pv = mor_b200.POD(X[:16], 5); mor_b200.reduce(pv, mor_b200.TSVD())
+    pu = mor_b200.POD(F.nonlinear_snapshots(X)[:16], 5); mor_b200.reduce(pu, mor_b200.TSVD())
+    idx = mor_b200.deim_interpolation_indices(pu.rbasis)
+    P = mor_b200.deim_projector(pu.rbasis, pv.rbasis, idx)
+    Pref = O.deim_projector(pu.rbasis, pv.rbasis, idx)
+    assert np.max(np.abs(P - Pref)) <= 1e-10 * np.max(np.abs(Pref))
+    # a singular selection is reported like the reference's SingularException
+    with pytest.raises(mor_b200.SingularError):
+        mor_b200.deim_projector(U, V, np.full(U.shape[1], 1, dtype=np.int64))
+
+
+def test_galerkin_projection_of_the_linear_part(gpu):
+    """deim.jl:154-155,261: A_hat = V'AV (A sparse CSC), g_hat = V'g, y_hat(0) = V'snapshot[:,1]."""
+    import scipy.sparse as sp
+    import fhn_fixture as F
+    rng = np.random.Generator(np.random.PCG64(5))
+    for (m, k, dens) in [(32, 5, 0.2), (2000, 12, 0.01), (150_001, 40, 2e-5)]:
+        nnz = int(dens * m * m)        # scattered entries + a second-difference stencil (a MOL operator)
+        A = sp.coo_matrix((rng.standard_normal(nnz), (rng.integers(0, m, nnz), rng.integers(0, m, nnz))),
+                          shape=(m, m)).tocsc() + \
+            sp.diags([np.full(m - 1, 1.0), np.full(m, -2.0), np.full(m - 1, 1.0)], [-1, 0, 1], format="csc")
+        V, _ = np.linalg.qr(rng.standard_normal((m, k)))
+        ref = V.T @ (A @ V)
+        got = mor_b200.galerkin_project(A, V)
+        assert got.shape == (k, k)
+        assert np.max(np.abs(got - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1.0)
+        g = rng.standard_normal(m)
+        assert np.max(np.abs(mor_b200.project(V, g) - V.T @ g)) <= 1e-12 * np.linalg.norm(g)
+        G2 = rng.standard_normal((m, 3))
+        assert np.max(np.abs(mor_b200.project(V, G2) - V.T @ G2)) <= 1e-12 * np.linalg.norm(G2)
+    X = F.snapshots()
+    pod = mor_b200.POD(X, 5); mor_b200.reduce(pod, mor_b200.TSVD())
+    y0 = mor_b200.project(pod.rbasis, X[:, 0])                       # deim.jl:261
+    assert np.max(np.abs(y0 - pod.rbasis.T @ X[:, 0])) <= 1e-13 * max(np.linalg.norm(X[:, 0]), 1.0)
+    with pytest.raises(ValueError):
+        mor_b200.galerkin_project(sp.eye(7, format="csc"), np.ones((8, 2)))
