@@ -347,6 +347,7 @@ def run_ours(args):
                    "steps": args.e2e_steps, "warmup": args.e2e_warmup, "host_memory": "pinned",
                    "api": "mor_b200_pod_factor + mor_b200_pod_basis (host pointers)"}
             lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
+            lib.mor_b200_trim()      # drop the parked 137 GB ingest copy before the next phases
     X.free(); U.free()
 
     # ---- RSVD (BASELINE config 4 at N = 8: 64M x 512, k = 64, p = 0): 8M rows per GPU ----------------

@@ -67,6 +67,10 @@ int32_t mor_b200_set_stream(void* cuda_stream);
 int32_t mor_b200_sync(void);
 /* Page-locked host staging memory (cudaHostAlloc): snapshots handed to the host-pointer entry
  * points from such a buffer move at full PCIe speed.  Optional -- any host pointer works. */
+/* Give cached device memory back to the driver: the stream-ordered work pool and the parked copy of
+ * the last large (> 8 GB) host-ingested matrix, kept so that the next call skips a ~0.4 s
+ * cudaMalloc/cudaFree pair.  Done automatically when an allocation fails and at shutdown. */
+int32_t mor_b200_trim(void);
 int32_t mor_b200_host_alloc(uint64_t bytes, void** out);
 int32_t mor_b200_host_free(void* p);
 

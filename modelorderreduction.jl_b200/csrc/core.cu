@@ -49,7 +49,32 @@ static void trim_pool() {
         cudaStreamSynchronize(g_ctx.stream);
         cudaMemPoolTrimTo(pool, 0);
     }
+    if (g_ctx.ingest_p) {
+        cudaFree(g_ctx.ingest_p);
+        g_ctx.ingest_p = nullptr;
+        g_ctx.ingest_bytes = 0;
+    }
     cudaGetLastError();
+}
+
+int32_t ingest_alloc(DevBuf& buf, size_t bytes) {
+    buf.release();
+    if (bytes <= POOL_LIMIT) return buf.alloc(bytes);   // small: the pool is already fast
+    if (g_ctx.ingest_p && g_ctx.ingest_bytes >= bytes) {
+        buf.p = g_ctx.ingest_p;
+        buf.bytes = g_ctx.ingest_bytes;
+        g_ctx.ingest_p = nullptr;
+        g_ctx.ingest_bytes = 0;
+    } else {
+        if (g_ctx.ingest_p) {
+            cudaFree(g_ctx.ingest_p);
+            g_ctx.ingest_p = nullptr;
+            g_ctx.ingest_bytes = 0;
+        }
+        MOR_TRY(buf.alloc(bytes));
+    }
+    buf.cacheable = true;
+    return MOR_OK;
 }
 
 int32_t DevBuf::alloc(size_t nbytes) {
@@ -71,9 +96,18 @@ int32_t DevBuf::alloc(size_t nbytes) {
 }
 void DevBuf::release() {
     if (p) {
-        if (pooled && g_ctx.ready) cudaFreeAsync(p, g_ctx.stream);
-        else cudaFree(p);
+        if (pooled && g_ctx.ready) {
+            cudaFreeAsync(p, g_ctx.stream);
+        } else if (cacheable && g_ctx.ready && bytes > g_ctx.ingest_bytes) {
+            if (g_ctx.ingest_p) cudaFree(g_ctx.ingest_p);   // park the larger buffer
+            cudaStreamSynchronize(g_ctx.stream);
+            g_ctx.ingest_p = p;
+            g_ctx.ingest_bytes = bytes;
+        } else {
+            cudaFree(p);
+        }
     }
+    cacheable = false;
     p = nullptr;
     bytes = 0;
     pooled = false;
@@ -214,6 +248,9 @@ int32_t mor_b200_shutdown(void) {
         if (g_ctx.scratch_p) cudaFree(g_ctx.scratch_p);
         g_ctx.scratch_p = nullptr;
         g_ctx.scratch_bytes = 0;
+        if (g_ctx.ingest_p) cudaFree(g_ctx.ingest_p);
+        g_ctx.ingest_p = nullptr;
+        g_ctx.ingest_bytes = 0;
         if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
         g_ctx.copy_stream = nullptr;
         if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
@@ -234,6 +271,12 @@ int32_t mor_b200_set_stream(void* cuda_stream) {
 int32_t mor_b200_sync(void) {
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return MOR_OK;
+}
+
+int32_t mor_b200_trim(void) {
+    MOR_TRY(require_ctx());
+    trim_pool();
     return MOR_OK;
 }
 

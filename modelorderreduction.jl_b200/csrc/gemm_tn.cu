@@ -26,7 +26,7 @@
 namespace mor {
 
 int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
-                        int ldc, int accumulate);  // gemm_tn_sk.cu
+                        int ldc, int accumulate, int mode);  // gemm_tn_sk.cu
 
 namespace {
 
@@ -280,11 +280,13 @@ int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ld
         return MOR_OK;
     }
     if (p <= 64 || q <= 64) return launch_tn<64, 64, 16, 32, 20, 5, 2>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
-    // The balanced stream-K variant (gemm_tn_sk.cu) is kept as an opt-in experiment: measured on
-    // B200 at 16M x 1024 it is SLOWER (705 ms vs 565 ms) -- it gives up the lock-step L2 sharing of
-    // the row groups, re-reads the matrix 9x from HBM in 160-byte pieces and becomes DRAM-page bound.
-    static const bool streamk = getenv("MOR_B200_GEMM_TN_STREAMK") != nullptr;
-    if (streamk) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
+    // The balanced variants (gemm_tn_sk.cu) are kept as opt-in experiments: measured on B200 at
+    // 16M x 1024 both are SLOWER than the lock-step kernel below (563 ms): tile-major stream-K 705 ms
+    // (gives up the L2 sharing of the row groups, re-reads the matrix 9x from HBM in 160-byte pieces),
+    // chunk-major 64 x 64 blocks 721 ms (keeps the sharing but doubles the L2->SM operand traffic and
+    // halves the DMMA work per TMA box / per fragment load).
+    static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");   // "0": tile-major stream-K, "1": chunk-major blocks
+    if (sk) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, atoi(sk));
     return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }
 

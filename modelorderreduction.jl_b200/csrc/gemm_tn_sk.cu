@@ -48,7 +48,8 @@ struct Seg {
 
 struct TileInfo {
     int a_col, b_col, small, diag;
-    int seg_begin, seg_end;
+    long long part_base;   // first partial tile of this output tile in the workspace (doubles)
+    int nparts;            // number of partial tiles, stored back to back
 };
 
 struct Maps {
@@ -175,8 +176,7 @@ gemm_tn_sk_kernel(const __grid_constant__ Maps maps, const Seg* __restrict__ seg
 }
 
 __global__ void __launch_bounds__(256)
-gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const Seg* __restrict__ segs,
-                         const TileInfo* __restrict__ tiles, int same, int p, int q, double* __restrict__ C, int ldc,
+gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const TileInfo* __restrict__ tiles, int same, int p, int q, double* __restrict__ C, int ldc,
                          int accumulate) {
     const TileInfo t = tiles[blockIdx.y];
     const int bm = t.small ? 64 : 128;
@@ -187,7 +187,8 @@ gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const Seg* __restrict_
     if (gi >= p || gj >= q) return;
     if (same && t.diag && r > c) return;  // written by the mirrored element: exact symmetry
     double s = 0.0;
-    for (int sg = t.seg_begin; sg < t.seg_end; ++sg) s += part[segs[sg].part_off + e];
+    const double* src = part + t.part_base + e;
+    for (int i = 0; i < t.nparts; ++i) s += src[(size_t)i * bm * bm];
     if (accumulate) s += C[(size_t)gj * ldc + gi];
     C[(size_t)gj * ldc + gi] = s;
     if (same && gi != gj) C[(size_t)gi * ldc + gj] = s;
@@ -196,13 +197,47 @@ gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const Seg* __restrict_
 }  // namespace
 
 // C (p x q) = A' * B, or the symmetric Gram matrix when A == B.  Requires p, q > 64.
+// mode 0: tile-major stream-K (128 x 128 tiles + split diagonal blocks, contiguous equal-cost pieces);
+// mode 1: chunk-major 64 x 64 blocks -- the rows are cut into NCH chunks, the work items (chunk, block)
+//         are dealt round-robin to the CTAs in chunk-major order, so all CTAs sweep the rows together
+//         (a panel is fetched from HBM about twice instead of 9x) and every SM gets the same number of
+//         equal-cost items to within one.
 int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
-                        int ldc, int accumulate) {
+                        int ldc, int accumulate, int mode) {
     Ctx& cx = ctx();
     const bool same = (A == B && lda == ldb && p == q);
     const long long P = (m + KB - 1) / KB;
-    // ---- tiles -------------------------------------------------------------------------------
     std::vector<TileInfo> tiles;
+    std::vector<Seg> segs;
+    std::vector<int> cta_seg(1, 0);
+    long long part_doubles = 0;
+    int nct = cx.num_sms;
+    if (mode == 1) {
+        const int bp = (p + 63) / 64, bq = (q + 63) / 64;
+        for (int bi = 0; bi < bp; ++bi)
+            for (int bj = same ? bi : 0; bj < bq; ++bj) tiles.push_back({bi * 64, bj * 64, 1, (same && bi == bj) ? 1 : 0, 0, 0});
+        const long long ntiles = (long long)tiles.size();
+        long long nch = (30LL * nct + ntiles - 1) / ntiles;      // ~30 items per CTA
+        nch = std::max<long long>(1, std::min(nch, P / 64));     // but at least 64 panels per item
+        for (long long t = 0; t < ntiles; ++t) {
+            tiles[t].part_base = t * nch * 4096;
+            tiles[t].nparts = (int)nch;
+        }
+        part_doubles = ntiles * nch * 4096;
+        const long long nitems = ntiles * nch;
+        if (nitems < nct) nct = (int)nitems;
+        cta_seg.clear();
+        for (int c = 0; c < nct; ++c) {
+            cta_seg.push_back((int)segs.size());
+            for (long long id = c; id < nitems; id += nct) {
+                const long long ch = id / ntiles, t = id % ntiles;
+                segs.push_back({tiles[t].a_col, tiles[t].b_col, 1, tiles[t].diag, P * ch / nch, P * (ch + 1) / nch,
+                                tiles[t].part_base + ch * 4096});
+            }
+        }
+        cta_seg.push_back((int)segs.size());
+    } else {
+    // ---- tiles -------------------------------------------------------------------------------
     const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
     for (int ti = 0; ti < tp; ++ti)
         for (int tj = same ? ti : 0; tj < tq_; ++tj) {
@@ -220,16 +255,13 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
     // ---- equal-cost contiguous pieces, one per SM ----------------------------------------------
     long long total = 0;
     for (const TileInfo& t : tiles) total += (t.small ? 1 : 4) * P;
-    int nct = cx.num_sms;
     if (total < (long long)nct * 16) nct = (int)std::max<long long>(1, total / 16);  // tiny problems: fewer CTAs
-    std::vector<Seg> segs;
-    std::vector<int> cta_seg(1, 0);
-    long long part_doubles = 0;
     int cta = 0;
     long long quota = (total + nct - 1) / nct, left = quota;
     for (TileInfo& t : tiles) {
         const int cost = t.small ? 1 : 4;
-        t.seg_begin = (int)segs.size();
+        t.part_base = part_doubles;
+        t.nparts = 0;
         long long pb = 0;
         while (pb < P) {
             const bool last = (cta + 1 >= nct);
@@ -242,12 +274,13 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
             const long long take = last ? (P - pb) : std::min(P - pb, left / cost);
             segs.push_back({t.a_col, t.b_col, t.small, t.diag, pb, pb + take, part_doubles});
             part_doubles += t.small ? 64 * 64 : 128 * 128;
+            ++t.nparts;
             pb += take;
             left -= take * cost;
         }
-        t.seg_end = (int)segs.size();
     }
     while ((int)cta_seg.size() < nct + 1) cta_seg.push_back((int)segs.size());
+    }
     segs.push_back({0, 0, 0, 0, 0, 0, 0});  // sentinel for the producer cursor
 
     Maps maps;
@@ -278,7 +311,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
     }
     gemm_tn_sk_kernel<<<nct, 256, SK_SMEM, cx.stream>>>(maps, d_segs, d_cta, part);
     MOR_CUDA(cudaGetLastError());
-    gemm_tn_sk_reduce_kernel<<<dim3(64, (unsigned)tiles.size()), 256, 0, cx.stream>>>(part, d_segs, d_tiles, same ? 1 : 0,
+    gemm_tn_sk_reduce_kernel<<<dim3(64, (unsigned)tiles.size()), 256, 0, cx.stream>>>(part, d_tiles, same ? 1 : 0,
                                                                                    p, q, C, ldc, accumulate);
     MOR_CUDA(cudaGetLastError());
     count_launch(2);

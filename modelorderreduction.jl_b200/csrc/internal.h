@@ -46,6 +46,8 @@ struct Ctx {
     int64_t launches = 0;
     void* scratch_p = nullptr;          // grow-only workspace (partial tiles, packed W)
     size_t scratch_bytes = 0;
+    void* ingest_p = nullptr;           // parked device copy of the last large host-ingested matrix:
+    size_t ingest_bytes = 0;            // cudaMalloc/cudaFree of 137 GB cost ~0.4 s per call otherwise
 };
 Ctx& ctx();
 int32_t require_ctx();
@@ -53,6 +55,9 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 // Grow-only device workspace of at least `bytes`; contents are only valid until the next
 // scratch() call on this context (all users are ordered on ctx().stream).
 int32_t scratch(size_t bytes, void** out);
+// Device buffer for a host-ingested snapshot matrix: reuses the parked one when it is large enough.
+struct DevBuf;
+int32_t ingest_alloc(DevBuf& buf, size_t bytes);
 
 // Debug stopwatch: when MOR_B200_DEBUG is set, lap("label") synchronises the stream and prints the
 // wall time since the previous lap to stderr (serialises the pipeline: for diagnosis only).
@@ -68,6 +73,7 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     bool pooled = false;   // from the stream-ordered pool (freed with cudaFreeAsync)
+    bool cacheable = false; // a large host-ingest copy: parked in the context for the next call on release
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -76,8 +82,8 @@ struct DevBuf {
     void release();
     void take(DevBuf& o) {  // move ownership
         release();
-        p = o.p; bytes = o.bytes; pooled = o.pooled;
-        o.p = nullptr; o.bytes = 0; o.pooled = false;
+        p = o.p; bytes = o.bytes; pooled = o.pooled; cacheable = o.cacheable;
+        o.p = nullptr; o.bytes = 0; o.pooled = false; o.cacheable = false;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };

@@ -552,7 +552,7 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
     tm.total.start();
     const int64_t ld = std::max<int64_t>((m + 1) & ~int64_t(1), 2);
     DevBuf dX, dOm, Gacc;
-    MOR_TRY(dX.alloc(sizeof(double) * (size_t)ld * (size_t)n));
+    MOR_TRY(ingest_alloc(dX, sizeof(double) * (size_t)ld * (size_t)n));
     if (ld != m)  // keep the pad row finite
         MOR_CUDA(cudaMemset2DAsync(dX.as<double>() + m, (size_t)ld * 8, 0, 8, (size_t)n, cx.stream));
     // Pipelined ingest (tall SVD/TSVD of a Matrix): rows travel in ~1 GiB chunks on a copy

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mor_b200_last_error": (C.c_char_p, []),
     "mor_b200_set_stream": (_i32, [_p]),
     "mor_b200_sync": (_i32, []),
+    "mor_b200_trim": (_i32, []),
     "mor_b200_host_alloc": (_i32, [_u64, C.POINTER(_p)]),
     "mor_b200_host_free": (_i32, [_p]),
     "mor_b200_comm_unique_id": (_i32, [_p]),
