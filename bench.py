@@ -158,7 +158,7 @@ def run_reference(args):
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample,
                              "extrapolated_full_ms": pod_flops(M_FULL, N_COLS, K_MODES) / (tf * 1e12) * 1e3},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -350,6 +350,24 @@ def run_ours(args):
             lib.mor_b200_trim()      # drop the parked 137 GB ingest copy before the next phases
     X.free(); U.free()
 
+    # ---- known-answer run at FULL size: X = H_u [S V'; 0] (exact singular values / left vectors) -------
+    kat = None
+    if not args.no_kat:
+        Xk = DeviceMatrix.alloc(m_loc, n).synth(_lib.SYNTH_KAT, seed=7, global_row0=row0, param=3.0)
+        Uk = DeviceMatrix.alloc(m_loc, k)
+        barrier()
+        t0 = time.perf_counter()
+        fk = pod_factor_dev(Xk, _lib.MOR_SVD, k, flags=_lib.POD_MAY_OVERWRITE, m_global=M)
+        fk.basis(k, Uk)
+        barrier()
+        kat_ms = (time.perf_counter() - t0) * 1e3
+        s_exact = 10.0 ** (-3.0 * np.arange(n) / (n - 1))
+        kat = {"workload": f"{M}x{n} known-answer matrix (two Householder reflectors), k={k}",
+               "sigma_max_rel_err": float(np.max(np.abs(fk.s - s_exact) / s_exact)),
+               "left_vectors_max_abs_err": Uk.kat_check(k, n, seed=7, global_row0=row0, param=3.0),
+               "cholqr_passes": fk.info()[0], "jacobi_sweeps": fk.info()[1], "ms": kat_ms}
+        fk.free(); Xk.free(); Uk.free()
+
     # ---- RSVD (BASELINE config 4 at N = 8: 64M x 512, k = 64, p = 0): 8M rows per GPU ----------------
     rsvd = None
     if not args.no_rsvd:
@@ -459,11 +477,23 @@ def run_ours(args):
                                         "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
                          "frac": achieved / pk_t.value if pk_t.value else None, "traffic": None,
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
-            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "cpu_baseline": cpu}
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 during the run (NCCL
+    prints its version banner there) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -477,6 +507,7 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rsvd", action="store_true")
+    ap.add_argument("--no-kat", action="store_true")
     ap.add_argument("--rsvd-rows-per-gpu", type=int, default=8 * 2**20)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

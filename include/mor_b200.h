@@ -51,6 +51,9 @@ extern "C" {
 #define MOR_SYNTH_GRADED 0  /* N(0,1) * 10^(-param * j/(n-1)) per column j            */
 #define MOR_SYNTH_GAUSS 1   /* N(0,1) * param                                          */
 #define MOR_SYNTH_LOWRANK 2 /* graded, but the first `iparam` columns have scale 1     */
+#define MOR_SYNTH_KAT 3     /* known-answer matrix H_u [S V'; 0]: singular values exactly 10^(-param j/(n-1)),
+                               left vectors the columns of the Householder reflector H_u.  COLLECTIVE over
+                               the ranks (one all-reduce); every rank passes its own global_row0            */
 
 typedef struct mor_pod_s* mor_pod_t; /* factorisation handle (owns device memory)  */
 typedef struct mor_mat_s* mor_mat_t; /* device-resident column-major FP64 matrix   */
@@ -145,6 +148,10 @@ int32_t mor_b200_mat_download(mor_mat_t a, double* host, int64_t ldh);
  * the value of an entry depends only on (seed, global row, column): shard invariant. */
 int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_row0,
                        double param, int64_t iparam);
+/* Known-answer check for MOR_SYNTH_KAT: max over all ranks, rows and the first k columns of
+ * |U[i][j] -+ (H_u e_j)[i]| for this rank's row shard U of the computed left vectors (collective). */
+int32_t mor_b200_kat_check(mor_mat_t U, int64_t k, int64_t n, uint64_t seed, int64_t global_row0, double param,
+                           double* max_err);
 /* flags for pod_factor_dev */
 #define MOR_POD_MAY_OVERWRITE 1 /* X may be overwritten by X*inv(R) when >1 pass is needed */
 #define MOR_POD_FORCE_TWO_PASS 2 /* always run CholeskyQR2 (never stop after one Gram pass) */

@@ -403,4 +403,12 @@ int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_
     return MOR_OK;
 }
 
+int32_t mor_b200_kat_check(mor_mat_t U, int64_t k, int64_t n, uint64_t seed, int64_t global_row0, double param,
+                           double* max_err) {
+    MOR_ARG(U != nullptr && max_err != nullptr && k >= 1 && k <= U->n && n >= k && global_row0 >= 0,
+            "mor_b200_kat_check: bad arguments");
+    MOR_TRY(require_ctx());
+    return kat_check_left(U->p, U->m, U->ld, (int)k, n, seed, global_row0, param, max_err);
+}
+
 }  // extern "C"

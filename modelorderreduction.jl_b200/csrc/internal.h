@@ -122,6 +122,8 @@ int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, ui
                    int64_t row0, double param, int64_t iparam);
 int32_t fill_normal(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0,
                     double scale);
+int32_t kat_check_left(const double* U, int64_t m, int64_t ld, int k, int64_t n, uint64_t seed, int64_t row0,
+                       double decades, double* max_err);
 
 // ---- DEIM (deim.cu) -------------------------------------------------------------------------
 int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host);

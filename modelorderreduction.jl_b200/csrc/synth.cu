@@ -1,6 +1,7 @@
 // Synthetic snapshot generators: counter-based Philox4x32-10, so the
 // value of entry (global row, column) depends only on the seed -- the same matrix is
 // produced for any number of row shards.  HBM write-bound.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -82,6 +83,8 @@ static int32_t launch_synth(double* X, int64_t m, int64_t n, int64_t ld, uint64_
     return MOR_OK;
 }
 
+int32_t kat_fill(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double decades);
+
 int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, uint64_t seed,
                    int64_t row0, double param, int64_t iparam) {
     std::vector<double> scale((size_t)(n > 0 ? n : 1), 1.0);
@@ -102,11 +105,209 @@ int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, ui
                 }
             }
             break;
+        case MOR_SYNTH_KAT:
+            return kat_fill(X, m, n, ld, seed, row0, param);
         default:
             set_error("mor_b200_synth: unknown generator kind");
             return MOR_ERR_ARG;
     }
     return launch_synth(X, m, n, ld, seed, row0, scale);
+}
+
+// ---- known-answer matrix (SURVEY.md section 8d "KAT at full size") -------------------------------
+//   X = H_u * [S V'; 0],  H_u = I - 2 u u' (u = z / ||z||, z Philox N(0,1) over the M global rows),
+//   V' = I - 2 v v' (v_j ~ cos(j + 1), normalised),  S = diag(10^(-param j / (n - 1))).
+// Its singular values are exactly S (up to the rounding of the entries), its left vectors the
+// columns of H_u, its right vectors the columns of V -- at any size and for any row sharding.
+// Not a column scaling of a well-conditioned matrix: it exercises the multi-pass CholeskyQR path.
+__device__ __forceinline__ double kat_z(uint64_t seed, int64_t grow) {
+    const int64_t gb = grow >> 2;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 r = philox4x32_10(make_uint4((uint32_t)gb, (uint32_t)(gb >> 32), 0xffffffffu, 0x6b6174u), key);
+    float z[4];
+    normal4(r, z);
+    return (double)z[grow & 3];
+}
+
+__global__ void __launch_bounds__(256)
+kat_sumsq_kernel(uint64_t seed, int64_t row0, int64_t m, double* __restrict__ out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const double z = kat_z(seed, row0 + i);
+        s = fma(z, z, s);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+__global__ void kat_top_kernel(uint64_t seed, int n, double* __restrict__ ztop) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ztop[i] = kat_z(seed, i);
+}
+
+// reference left vector entry: (H_u e_j)[gi] = delta - 2 u_gi u_j
+__device__ __forceinline__ double kat_uref(uint64_t seed, int64_t gi, int j, double inv_norm, const double* utop) {
+    return (gi == j ? 1.0 : 0.0) - 2.0 * (kat_z(seed, gi) * inv_norm) * utop[j];
+}
+
+__global__ void __launch_bounds__(256)
+kat_fill_kernel(double* __restrict__ X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double inv_norm,
+                const double* __restrict__ sig, const double* __restrict__ v, const double* __restrict__ w) {
+    const int64_t total = m * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = t / m, lr = t - col * m, gi = row0 + lr;
+        double b = 0.0;
+        if (gi < n) b = sig[gi] * ((gi == col ? 1.0 : 0.0) - 2.0 * v[gi] * v[col]);
+        X[col * ld + lr] = b - 2.0 * (kat_z(seed, gi) * inv_norm) * w[col];
+    }
+}
+
+// d[j] += sum_i U[i][j] * uref(i, j)   (pass 0);   e[j] = max_i |U[i][j] - sgn[j] * uref(i, j)|  (pass 1)
+__global__ void __launch_bounds__(256)
+kat_check_kernel(const double* __restrict__ U, int64_t m, int64_t ld, uint64_t seed, int64_t row0, double inv_norm,
+                 const double* __restrict__ utop, int pass, const double* __restrict__ sgn, double* __restrict__ out) {
+    __shared__ double red[8];
+    const int j = blockIdx.y;
+    const double* u = U + (size_t)j * ld;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const double r = kat_uref(seed, row0 + i, j, inv_norm, utop);
+        if (pass == 0) s = fma(u[i], r, s);
+        else s = fmax(s, fabs(u[i] - sgn[j] * r));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, s, off);
+        s = pass == 0 ? s + o : fmax(s, o);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = red[0];
+        for (int w = 1; w < 8; ++w) t = pass == 0 ? t + red[w] : fmax(t, red[w]);
+        if (pass == 0) atomicAdd(&out[j], t);
+        else atomicMax(reinterpret_cast<unsigned long long*>(&out[j]), (unsigned long long)__double_as_longlong(t));
+    }
+}
+
+struct KatSetup {
+    double inv_norm;
+    std::vector<double> utop, sig, v, w;
+};
+
+// collective over the ranks (one all-reduce of ||z||^2)
+static int32_t kat_setup(int64_t m_local, int64_t row0, int64_t n, uint64_t seed, double decades, KatSetup* ks) {
+    Ctx& c = ctx();
+    DevBuf acc, ztop;
+    MOR_TRY(acc.alloc(sizeof(double)));
+    MOR_TRY(ztop.alloc(sizeof(double) * (size_t)n));
+    MOR_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), c.stream));
+    if (m_local > 0) kat_sumsq_kernel<<<c.num_sms * 8, 256, 0, c.stream>>>(seed, row0, m_local, acc.as<double>());
+    kat_top_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(seed, (int)n, ztop.as<double>());
+    count_launch(2);
+    MOR_CUDA(cudaGetLastError());
+    MOR_TRY(comm_allreduce_sum(acc.as<double>(), 1));
+    double zz = 0.0;
+    std::vector<double> z((size_t)n);
+    MOR_CUDA(cudaMemcpyAsync(&zz, acc.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    MOR_CUDA(cudaMemcpyAsync(z.data(), ztop.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    MOR_ARG(zz > 0.0, "known-answer matrix: empty");
+    ks->inv_norm = 1.0 / std::sqrt(zz);
+    ks->utop.resize((size_t)n);
+    ks->sig.resize((size_t)n);
+    ks->v.resize((size_t)n);
+    ks->w.resize((size_t)n);
+    double vn = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        ks->utop[j] = z[j] * ks->inv_norm;
+        ks->sig[j] = n > 1 ? std::pow(10.0, -decades * (double)j / (double)(n - 1)) : 1.0;
+        ks->v[j] = std::cos((double)(j + 1));
+        vn += ks->v[j] * ks->v[j];
+    }
+    vn = 1.0 / std::sqrt(vn);
+    double t = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        ks->v[j] *= vn;
+        t += ks->sig[j] * ks->utop[j] * ks->v[j];
+    }
+    for (int64_t j = 0; j < n; ++j) ks->w[j] = ks->sig[j] * ks->utop[j] - 2.0 * ks->v[j] * t;
+    return MOR_OK;
+}
+
+static int32_t upload(const std::vector<double>& h, DevBuf& d) {
+    MOR_TRY(d.alloc(sizeof(double) * h.size()));
+    MOR_CUDA(cudaMemcpyAsync(d.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx().stream));
+    return MOR_OK;
+}
+
+int32_t kat_fill(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double decades) {
+    Ctx& c = ctx();
+    KatSetup ks;
+    MOR_TRY(kat_setup(m, row0, n, seed, decades, &ks));
+    DevBuf ds, dv, dw;
+    MOR_TRY(upload(ks.sig, ds));
+    MOR_TRY(upload(ks.v, dv));
+    MOR_TRY(upload(ks.w, dw));
+    if (m > 0 && n > 0) {
+        kat_fill_kernel<<<c.num_sms * 16, 256, 0, c.stream>>>(X, m, n, ld, seed, row0, ks.inv_norm, ds.as<double>(),
+                                                             dv.as<double>(), dw.as<double>());
+        count_launch();
+        MOR_CUDA(cudaGetLastError());
+    }
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    return MOR_OK;
+}
+
+// max_i,j<k |U[i][j] -+ (H_u e_j)[i]| over ALL ranks (collective); U is this rank's row shard
+int32_t kat_check_left(const double* U, int64_t m, int64_t ld, int k, int64_t n, uint64_t seed, int64_t row0,
+                       double decades, double* max_err) {
+    Ctx& c = ctx();
+    MOR_ARG(k >= 1 && k <= n, "kat_check: k must be in 1..n");
+    KatSetup ks;
+    MOR_TRY(kat_setup(m, row0, n, seed, decades, &ks));
+    DevBuf du, dd, de;
+    MOR_TRY(upload(ks.utop, du));
+    MOR_TRY(dd.alloc(sizeof(double) * (size_t)k));
+    MOR_TRY(de.alloc(sizeof(double) * (size_t)k));
+    MOR_CUDA(cudaMemsetAsync(dd.p, 0, sizeof(double) * (size_t)k, c.stream));
+    MOR_CUDA(cudaMemsetAsync(de.p, 0, sizeof(double) * (size_t)k, c.stream));
+    dim3 grid(c.num_sms, (unsigned)k);
+    if (m > 0) kat_check_kernel<<<grid, 256, 0, c.stream>>>(U, m, ld, seed, row0, ks.inv_norm, du.as<double>(), 0, nullptr, dd.as<double>());
+    MOR_TRY(comm_allreduce_sum(dd.as<double>(), (size_t)k));
+    std::vector<double> d((size_t)k);
+    MOR_CUDA(cudaMemcpyAsync(d.data(), dd.p, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, c.stream));
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    for (double& x : d) x = x < 0.0 ? -1.0 : 1.0;
+    MOR_CUDA(cudaMemcpyAsync(dd.p, d.data(), sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, c.stream));
+    if (m > 0) kat_check_kernel<<<grid, 256, 0, c.stream>>>(U, m, ld, seed, row0, ks.inv_norm, du.as<double>(), 1, dd.as<double>(), de.as<double>());
+    count_launch(2);
+    MOR_CUDA(cudaGetLastError());
+    std::vector<double> e((size_t)k);
+    MOR_CUDA(cudaMemcpyAsync(e.data(), de.p, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, c.stream));
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    double mx = 0.0;
+    for (double x : e) mx = std::max(mx, x);
+    // max over ranks through a sum all-reduce of a one-hot vector (NCCL has MAX, but this keeps one collective type)
+    DevBuf slots;
+    MOR_TRY(slots.alloc(sizeof(double) * (size_t)c.nranks));
+    std::vector<double> one((size_t)c.nranks, 0.0);
+    one[(size_t)c.rank] = mx;
+    MOR_CUDA(cudaMemcpyAsync(slots.p, one.data(), sizeof(double) * (size_t)c.nranks, cudaMemcpyHostToDevice, c.stream));
+    MOR_TRY(comm_allreduce_sum(slots.as<double>(), (size_t)c.nranks));
+    MOR_CUDA(cudaMemcpyAsync(one.data(), slots.p, sizeof(double) * (size_t)c.nranks, cudaMemcpyDeviceToHost, c.stream));
+    MOR_CUDA(cudaStreamSynchronize(c.stream));
+    for (double x : one) mx = std::max(mx, x);
+    *max_err = mx;
+    return MOR_OK;
 }
 
 int32_t fill_normal(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double scale) {

@@ -13,7 +13,7 @@ DEFAULT_LIB = _PKG_ROOT / "lib" / "libmor_b200.so"
 # status codes (include/mor_b200.h)
 OK, ERR_ARG, ERR_NONFINITE, ERR_CUDA, ERR_NOMEM, ERR_NOCONV, ERR_SINGULAR = range(7)
 MOR_SVD, MOR_TSVD, MOR_RSVD = 0, 1, 2
-SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK = 0, 1, 2
+SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK, SYNTH_KAT = 0, 1, 2, 3
 POD_MAY_OVERWRITE, POD_FORCE_TWO_PASS = 1, 2
 T_SLOTS = ("total", "h2d", "gram", "apply", "core", "basis", "comm", "deim_step", "deim_tail",
            "d2h", "sketch")
@@ -71,6 +71,7 @@ SIGNATURES = {
     "mor_b200_mat_upload": (_i32, [_p, _p, _i64]),
     "mor_b200_mat_download": (_i32, [_p, _p, _i64]),
     "mor_b200_synth": (_i32, [_p, _i32, _u64, _i64, _dbl, _i64]),
+    "mor_b200_kat_check": (_i32, [_p, _i64, _i64, _u64, _i64, _dbl, _pd]),
     "mor_b200_pod_factor_dev": (_i32, [_p, _i32, _i64, _i64, _p, _u64, _i32, C.POINTER(_p), _p,
                                        _pi64]),
     "mor_b200_pod_basis_dev": (_i32, [_p, _i64, _p]),

@@ -60,6 +60,12 @@ class DeviceMatrix:
         _lib.check(_lib.load().mor_b200_synth(self.handle, kind, seed, global_row0, param, iparam))
         return self
 
+    def kat_check(self, k: int, n: int, seed: int, global_row0: int = 0, param: float = 3.0) -> float:
+        """For left vectors computed from a SYNTH_KAT matrix: max |U[i][j] -+ (H_u e_j)[i]| (collective)."""
+        err = C.c_double(0.0)
+        _lib.check(_lib.load().mor_b200_kat_check(self.handle, k, n, seed, global_row0, param, C.byref(err)))
+        return err.value
+
     def free(self):
         if self.handle:
             _lib.load().mor_b200_mat_free(self.handle)

@@ -231,3 +231,21 @@ def test_fitzhugh_nagumo_pod5_deim5(gpu):
     assert idx.tolist() == O.deim_interpolation_indices(ub.rbasis).tolist()
     assert idx.tolist() == O.deim_interpolation_indices(uo.rbasis * np.sign((uo.rbasis * ub.rbasis).sum(0))).tolist()
     assert len(set(idx.tolist())) == 5 and 1 <= idx.min() and idx.max() <= 16
+
+
+def test_known_answer_matrix(gpu):
+    """X = H_u [S V'; 0] generated on the device (Householder reflectors: singular values and left
+    vectors known in closed form at ANY size -- SURVEY 8d 'KAT').  First the generator itself against
+    LAPACK at a small size, then the library at 2M rows, where no CPU oracle is practical."""
+    n = 24
+    Xs = DeviceMatrix.alloc(1001, n).synth(_lib.SYNTH_KAT, seed=9, param=3.0)
+    s_exact = 10.0 ** (-3.0 * np.arange(n) / (n - 1))
+    assert np.max(np.abs(sla.svd(Xs.to_host(), compute_uv=False) - s_exact)) < 1e-14
+    m, n, k = 2_000_003, 256, 32
+    X = DeviceMatrix.alloc(m, n).synth(_lib.SYNTH_KAT, seed=9, param=3.0)
+    f = pod_factor_dev(X, _lib.MOR_SVD, k, flags=_lib.POD_MAY_OVERWRITE)
+    s_exact = 10.0 ** (-3.0 * np.arange(n) / (n - 1))
+    assert f.info()[0] >= 2                              # not a column scaling: CholeskyQR2 path
+    assert O.sigma_error(s_exact, f.s) <= SIGMA_TOL
+    U = f.basis(k, DeviceMatrix.alloc(m, k))
+    assert U.kat_check(k, n, seed=9, param=3.0) <= ANGLE_TOL
