@@ -284,8 +284,12 @@ int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ld
     // 16M x 1024 both are SLOWER than the lock-step kernel below (563 ms): tile-major stream-K 705 ms
     // (gives up the L2 sharing of the row groups, re-reads the matrix 9x from HBM in 160-byte pieces),
     // chunk-major 64 x 64 blocks 721 ms (keeps the sharing but doubles the L2->SM operand traffic and
-    // halves the DMMA work per TMA box / per fragment load).
-    static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");   // "0": tile-major stream-K, "1": chunk-major blocks
+    // halves the DMMA work per TMA box / per fragment load); "2" = the classic schedule run through the
+    // segment kernel 570 ms (the machinery itself costs 1%); "3" = lock-step primary work capped at the
+    // fair share + tails and split diagonal blocks handed to the spare SMs 670 ms (the 64 x 64 tiles run
+    // at ~0.73 of the 128 x 128 tile rate -- 40 instead of 160 DMMAs per panel barrier -- so the
+    // diagonal-block CTAs become the stragglers).
+    static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");   // "0".."3": experimental schedules, see above
     if (sk) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, atoi(sk));
     return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }

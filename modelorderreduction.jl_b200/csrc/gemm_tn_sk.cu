@@ -236,6 +236,104 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
             }
         }
         cta_seg.push_back((int)segs.size());
+    } else if (mode == 2 || mode == 3) {
+        // Lock-step first, balance second.  Primary assignment = the classic one: G row groups x one CTA
+        // per (128 x 128 tile | diagonal block), every CTA starting at the first panel of its group so the
+        // group sweeps its rows together and shares them through L2.  mode 3 then caps every CTA at the
+        // fair share Tq = total / #SMs: a primary CTA stops Tq worth of panels into its group, the cut-off
+        // tails go to a pool that is handed to the CTAs with spare capacity -- the diagonal-block CTAs
+        // (three 64 x 64 tiles = 3/4 of the work of a full tile) and the SMs the classic grid leaves idle.
+        // mode 2 = no cap (the classic schedule run through this kernel, for A/B timing).
+        struct Prim { int tile; };
+        std::vector<int> slot_tiles;                 // primary slots per group -> first tile index
+        std::vector<int> slot_ntiles;                // 1 (big tile) or up to 3 (split diagonal block)
+        const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
+        for (int ti = 0; ti < tp; ++ti)
+            for (int tj = same ? ti : 0; tj < tq_; ++tj) {
+                slot_tiles.push_back((int)tiles.size());
+                if (same && ti == tj && mode == 3) {
+                    const int c0 = ti * 128;
+                    tiles.push_back({c0, c0, 1, 1, 0, 0});
+                    int cnt = 1;
+                    if (c0 + 64 < p) {
+                        tiles.push_back({c0, c0 + 64, 1, 0, 0, 0});
+                        tiles.push_back({c0 + 64, c0 + 64, 1, 1, 0, 0});
+                        cnt = 3;
+                    }
+                    slot_ntiles.push_back(cnt);
+                } else {
+                    tiles.push_back({ti * 128, tj * 128, 0, (same && ti == tj) ? 1 : 0, 0, 0});
+                    slot_ntiles.push_back(1);
+                }
+            }
+        const int nslots = (int)slot_tiles.size();
+        int G = nct / nslots;
+        if (G < 1) G = 1;
+        if (G > P) G = (int)std::max<long long>(1, P);
+        const int nprim = G * nslots;
+        if (nprim > nct) nct = nprim;                // more tiles than SMs: several waves
+        long long total = 0;
+        for (const TileInfo& t : tiles) total += (t.small ? 1 : 4) * P;
+        const long long Tq = (mode == 3) ? (total + nct - 1) / nct : (long long)4 * P + 1;
+        struct Piece { int tile; long long a, b; };
+        std::vector<std::vector<Piece>> work((size_t)nct);
+        std::vector<long long> left((size_t)nct, Tq);
+        std::vector<Piece> pool;
+        for (int g = 0; g < G; ++g) {
+            const long long ga = P * g / G, gb = P * (g + 1) / G;
+            for (int sl = 0; sl < nslots; ++sl) {
+                const int c = g * nslots + sl;
+                for (int u = 0; u < slot_ntiles[sl]; ++u) {
+                    const int t = slot_tiles[sl] + u;
+                    const int cost = tiles[t].small ? 1 : 4;
+                    long long take = std::min(gb - ga, left[c] / cost);
+                    if (take > 0) {
+                        work[c].push_back({t, ga, ga + take});
+                        left[c] -= take * cost;
+                    }
+                    if (ga + take < gb) pool.push_back({t, ga + take, gb});
+                }
+            }
+        }
+        // hand the pool to the CTAs with spare capacity (round-robin over them, largest spare first is
+        // not needed: pieces are split freely); the last candidate takes whatever rounding leaves over
+        int c = 0;
+        for (Piece pc : pool) {
+            const int cost = tiles[pc.tile].small ? 1 : 4;
+            int guard = 0;
+            while (pc.a < pc.b) {
+                if (left[c] < (long long)cost * 4 && guard < nct) {   // too little room for a useful slice
+                    c = (c + 1) % nct;
+                    ++guard;
+                    continue;
+                }
+                const long long take = guard >= nct ? pc.b - pc.a : std::min(pc.b - pc.a, left[c] / cost);
+                work[c].push_back({pc.tile, pc.a, pc.a + take});
+                left[c] -= take * cost;
+                pc.a += take;
+                guard = 0;
+            }
+        }
+        // partial-tile slots: contiguous per tile
+        std::vector<int> count(tiles.size(), 0);
+        for (const auto& wl : work)
+            for (const Piece& pc : wl) ++count[(size_t)pc.tile];
+        for (size_t t = 0; t < tiles.size(); ++t) {
+            tiles[t].part_base = part_doubles;
+            tiles[t].nparts = count[t];
+            part_doubles += (long long)count[t] * (tiles[t].small ? 4096 : 16384);
+            count[t] = 0;
+        }
+        cta_seg.clear();
+        for (int cc = 0; cc < nct; ++cc) {
+            cta_seg.push_back((int)segs.size());
+            for (const Piece& pc : work[(size_t)cc]) {
+                const TileInfo& t = tiles[(size_t)pc.tile];
+                segs.push_back({t.a_col, t.b_col, t.small, t.diag, pc.a, pc.b,
+                                t.part_base + (long long)count[(size_t)pc.tile]++ * (t.small ? 4096 : 16384)});
+            }
+        }
+        cta_seg.push_back((int)segs.size());
     } else {
     // ---- tiles -------------------------------------------------------------------------------
     const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
