@@ -249,3 +249,38 @@ def test_known_answer_matrix(gpu):
     assert O.sigma_error(s_exact, f.s) <= SIGMA_TOL
     U = f.basis(k, DeviceMatrix.alloc(m, k))
     assert U.kat_check(k, n, seed=9, param=3.0) <= ANGLE_TOL
+
+
+def test_abi_error_paths(gpu):
+    """Status codes of the C ABI (include/mor_b200.h): bad arguments are reported, never crash."""
+    import ctypes as C
+    lib = gpu
+    X = graded(500, 6, 1, 0)
+    s = np.empty(6); nS = C.c_int64(0); h = C.c_void_p()
+    args = (X.ctypes.data, 500, 6, 500)
+    assert lib.mor_b200_pod_factor(*args, _lib.MOR_TSVD, 0, 0, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert lib.mor_b200_pod_factor(*args, _lib.MOR_TSVD, 7, 0, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert lib.mor_b200_pod_factor(*args, _lib.MOR_RSVD, 2, -1, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert lib.mor_b200_pod_factor(*args, 7, 2, 0, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert lib.mor_b200_pod_factor(None, 500, 6, 500, _lib.MOR_SVD, 2, 0, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert lib.mor_b200_pod_factor(X.ctypes.data, 500, 6, 499, _lib.MOR_SVD, 2, 0, None, 0, C.byref(h), s.ctypes.data, C.byref(nS)) == _lib.ERR_ARG
+    assert b"" != lib.mor_b200_last_error()
+    f = _factor(X, _lib.MOR_TSVD, 3)
+    U = np.empty((500, 6), order="F")
+    assert lib.mor_b200_pod_basis(f.handle, 7, U.ctypes.data, 500, None, 0) == _lib.ERR_ARG     # only 6 triplets exist
+    assert lib.mor_b200_pod_basis(f.handle, 3, U.ctypes.data, 499, None, 0) == _lib.ERR_ARG     # ldu < m
+    assert lib.mor_b200_pod_basis(f.handle, 3, U.ctypes.data, 500, None, 0) == _lib.OK
+    f.close()
+    assert lib.mor_b200_pod_free(None) == _lib.OK
+    # a borrowed device matrix with an odd leading dimension cannot feed the TMA kernels: reported
+    d = DeviceMatrix.alloc(11, 4)
+    _, _, _, ptr = d.info
+    w = DeviceMatrix.wrap(ptr, 5, 4, 11)
+    with pytest.raises(ValueError):
+        pod_factor_dev(w, _lib.MOR_SVD, 2)
+    # a wide matrix and an empty one
+    with pytest.raises(ValueError):
+        mor_b200.deim_interpolation_indices(np.zeros((4, 0), order="F"))
+    idx = np.zeros(1025, dtype=np.int64)
+    B = np.zeros((2000, 1025), order="F")
+    assert lib.mor_b200_deim_indices(B.ctypes.data, 2000, 1025, 2000, idx.ctypes.data) == _lib.ERR_ARG
