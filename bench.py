@@ -445,7 +445,11 @@ def run_ours(args):
                          "achieved": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9,
                          "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                          "frac": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9 / hbm_peak,
-                         "live_read_peak_gbs": pk_g.value, "traffic": None},
+                         "live_read_peak_gbs": pk_g.value,
+                         # ncu --set full of greedy step 201 at 4,194,304 rows: 6.7504 GB read+written for
+                         # 6.7444 GB algorithmic (profiles/r01_ncu_summary.txt): 1.001 x, summed over the k launches
+                         "traffic": 1.001 * deim_bytes(Md, kd) / world,
+                         "traffic_note": "ncu-measured 1.001 x algorithmic bytes (one launch), applied to all k launches"},
             "tail_ms": dacc["deim_tail"] / args.steps, "e2e": deim_e2e}
     B.free()
     if world > 1:
@@ -475,7 +479,11 @@ def run_ours(args):
                          "achieved": achieved, "peak": pk_t.value, "unit": "TFLOP/s",
                          "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark in this run (MEASURED_PEAKS.json "
                                         "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
-                         "frac": achieved / pk_t.value if pk_t.value else None, "traffic": None,
+                         "frac": achieved / pk_t.value if pk_t.value else None,
+                         # dram__bytes_read+write of this kernel per launch: ncu --set full at 2,097,152 rows gave
+                         # 17.575 GB for 17.180 GB of operand (profiles/r01_ncu_final.txt); linear in the rows
+                         "traffic": 1.02300 * 8.0 * m_loc * n,
+                         "traffic_note": "ncu-measured 1.023 x (8 m n) bytes at 2M rows, scaled to this launch's rows",
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
             "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "cpu_baseline": cpu}
     emit(line)
