@@ -30,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "modelorderreduction.jl_b200", "python"))
 
 M_FULL, N_COLS, K_MODES = 16 * 2**20, 1024, 64
 DEIM_M, DEIM_K = 16 * 2**20, 256
+TRAFFIC_RATIO_GRAM = 3.475   # ncu: 59.70 GB for 17.18 GB of operand at 2M rows (balanced schedule: tails re-read from HBM)
 METRIC = "POD SVD() FP64 TFLOP/s at 16Mx1024 (algorithmic 2mn^2+2mnk flop / time); DEIM k=256 ms and HBM GB/s alongside"
 
 
@@ -475,15 +476,15 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": pod_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<128,128,...> (symmetric Gram, DMMA.8x8x4)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_sk_kernel (symmetric Gram, DMMA.8x8x4, balanced lock-step schedule) + reduce",
                          "achieved": achieved, "peak": pk_t.value, "unit": "TFLOP/s",
                          "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark in this run (MEASURED_PEAKS.json "
                                         "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
                          "frac": achieved / pk_t.value if pk_t.value else None,
-                         # dram__bytes_read+write of this kernel per launch: ncu --set full at 2,097,152 rows gave
-                         # 17.575 GB for 17.180 GB of operand (profiles/r01_ncu_final.txt); linear in the rows
-                         "traffic": 1.02300 * 8.0 * m_loc * n,
-                         "traffic_note": "ncu-measured 1.023 x (8 m n) bytes at 2M rows, scaled to this launch's rows",
+                         # dram bytes of this kernel per launch from ncu --set full at 2,097,152 rows
+                         # (profiles/r01_ncu_final.txt), linear in the rows
+                         "traffic": TRAFFIC_RATIO_GRAM * 8.0 * m_loc * n,
+                         "traffic_note": f"ncu-measured {TRAFFIC_RATIO_GRAM:.3f} x (8 m n) bytes at 2M rows, scaled to this launch's rows",
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
             "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "cpu_baseline": cpu}
     emit(line)

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -280,17 +281,18 @@ int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ld
         return MOR_OK;
     }
     if (p <= 64 || q <= 64) return launch_tn<64, 64, 16, 32, 20, 5, 2>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
-    // The balanced variants (gemm_tn_sk.cu) are kept as opt-in experiments: measured on B200 at
-    // 16M x 1024 both are SLOWER than the lock-step kernel below (563 ms): tile-major stream-K 705 ms
-    // (gives up the L2 sharing of the row groups, re-reads the matrix 9x from HBM in 160-byte pieces),
-    // chunk-major 64 x 64 blocks 721 ms (keeps the sharing but doubles the L2->SM operand traffic and
-    // halves the DMMA work per TMA box / per fragment load); "2" = the classic schedule run through the
-    // segment kernel 570 ms (the machinery itself costs 1%); "3" = lock-step primary work capped at the
-    // fair share + tails and split diagonal blocks handed to the spare SMs 670 ms (the 64 x 64 tiles run
-    // at ~0.73 of the 128 x 128 tile rate -- 40 instead of 160 DMMAs per panel barrier -- so the
-    // diagonal-block CTAs become the stragglers).
-    static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");   // "0".."3": experimental schedules, see above
-    if (sk) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, atoi(sk));
+    // Outputs wider than 64 columns run the balanced segment kernel of gemm_tn_sk.cu, schedule 3:
+    // the lock-step (tile, row group) assignment of launch_tn below, but every CTA capped at the fair
+    // share of the work, diagonal blocks computed as upper triangles (17 instead of 32 DMMAs per warp
+    // and k-step), and the cut-off tails handed to the diagonal-block CTAs and to the SMs the plain
+    // grid leaves idle.  Measured on B200, Gram of 16M x 1024: 515 ms vs 563 ms for launch_tn.
+    // MOR_B200_GEMM_TN_STREAMK selects the other schedules that were tried (all pass the parity tests):
+    // "classic" = launch_tn 563 ms; "0" tile-major stream-K 705 ms (loses the L2 sharing of the row
+    // groups, re-reads the matrix 9x from HBM in 160-byte pieces); "1" chunk-major 64 x 64 blocks 721 ms
+    // (small tiles: twice the operand traffic, 40 instead of 160 DMMAs per panel barrier); "2" the
+    // classic schedule through the segment kernel 570 ms (the machinery costs 1%).
+    static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");
+    if (!sk || strcmp(sk, "classic") != 0) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, sk ? atoi(sk) : 3);
     return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }
 

@@ -1,27 +1,26 @@
-// gemm_tn, balanced ("stream-K") variant for outputs wider than 64 columns.  EXPERIMENT, off by
-// default (MOR_B200_GEMM_TN_STREAMK=1 enables it): correct (all parity tests pass with it) but
-// measured slower than the lock-step decomposition on B200, see the note at the end of this comment.
+// gemm_tn for outputs wider than 64 columns: the balanced "segment" kernel (default schedule: mode 3).
 //
 // The plain decomposition of gemm_tn.cu -- one CTA per (128 x 128 tile, row group), 36 upper
 // tiles x 4 groups = 144 CTAs at n = 1024 -- runs the DMMA pipe at ~100% on the SMs it uses (ncu:
 // sm__pipe_tensor_subpipe_dmma_cycles_active 97.3% = 144/148), but leaves 4 SMs idle and computes
-// the useless lower halves of the 8 diagonal tiles.  Here the (tile x row panel) work space is
-// flattened and cut into one equal-cost contiguous piece per SM:
-//   * off-diagonal tiles are 128 x 128 (8 warps x 32 x 64 register tiles), cost 4 per panel;
-//   * a diagonal 128 x 128 block is three 64 x 64 tiles (two on the diagonal, one above), 8 warps x
-//     16 x 32, cost 1 per panel each -- 25% less work than the full block;
-//   * every CTA walks its piece: for each segment (tile, panel range) it zeroes its accumulators,
-//     streams the panels through the same TMA ring as gemm_tn.cu (one elected producer lane,
-//     PREFETCH panels ahead, running across segment boundaries), and writes a partial tile;
-//   * a second kernel adds the partial tiles of every tile in a fixed order (deterministic) and
-//     mirrors the lower triangle.
-// A panel is now read from HBM by every tile that needs it (9x the matrix at n = 1024) instead of
-// once via L2 -- the price of balance.  MEASURED (B200, 16M x 1024): 705 ms vs 565 ms for the
-// lock-step kernel.  The 9x traffic arrives as 160-byte column pieces 134 MB apart, i.e. one DRAM row
-// activation per piece, and HBM delivers only ~1.8 TB/s of it: the kernel turns DRAM-bound.  Kept for
-// a later round (taller panels / a panel-blocked internal layout would be needed to make it pay).
+// the useless lower halves of the 8 diagonal tiles: 0.84 of the DMMA roofline on the kernel's own
+// minimal flops.  Here a CTA executes a LIST of segments (tile, panel range); for each segment it
+// zeroes its accumulators, streams the panels through the same TMA ring as gemm_tn.cu (one elected
+// producer lane, PREFETCH panels ahead, running across segment boundaries) and writes a partial tile;
+// a second kernel adds the partial tiles of every output tile in a fixed order (deterministic) and
+// mirrors the lower triangle.  Schedules (host side, gemm_tn_streamk):
+//   mode 3 (default)  lock-step first, balance second: the classic (tile, group) assignment, all CTAs
+//           of a group sweeping the same rows together (one HBM fetch per panel, shared through L2),
+//           but each CTA capped at the fair share total/#SMs; diagonal blocks are computed as upper
+//           triangles only (run_segment_tri: 17 instead of 32 DMMAs per warp and k-step, perfectly
+//           balanced over the 8 warps), and the cut-off tails of the off-diagonal tiles (13% of the
+//           rows) go to the diagonal-block CTAs and to the otherwise idle SMs.  515 ms vs 563 ms.
+//   mode 0  tile-major stream-K, mode 1 chunk-major 64 x 64 blocks, mode 2 classic schedule through
+//           this kernel: measured slower (705 / 721 / 570 ms), kept for reference.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -40,7 +39,7 @@ constexpr size_t SK_SMEM = (size_t)STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8 +
 
 struct Seg {
     int a_col, b_col;      // first column of the A / B operand block
-    int small;             // 0: 128 x 128 tile, 1: 64 x 64 tile
+    int small;             // 0: 128 x 128 tile, 1: 64 x 64 tile, 2: diagonal 128 x 128 block, upper triangle only
     int diag;              // A block == B block (only one is loaded)
     long long p_begin, p_end;
     long long part_off;    // offset (doubles) of this segment's partial tile in the workspace
@@ -71,11 +70,11 @@ struct Producer {
         const long long fill = j / STAGES;
         if (fill > 0) ptx::mbar_wait(&empty[s], (uint32_t)((fill - 1) & 1));
         double* dst = ring + (size_t)s * STAGE_DOUBLES;
-        const int bw = sg.small ? 64 : 128;
+        const int bw = sg.small == 1 ? 64 : 128;
         ptx::mbar_expect_tx(&full[s], (uint32_t)((sg.diag ? bw : 2 * bw) * KB * 8));
         const int row = (int)(panel * KB);
-        ptx::tma_load_2d(dst, sg.small ? &maps->a_small : &maps->a_big, row, sg.a_col, &full[s]);
-        if (!sg.diag) ptx::tma_load_2d(dst + bw * KB, sg.small ? &maps->b_small : &maps->b_big, row, sg.b_col, &full[s]);
+        ptx::tma_load_2d(dst, sg.small == 1 ? &maps->a_small : &maps->a_big, row, sg.a_col, &full[s]);
+        if (!sg.diag) ptx::tma_load_2d(dst + bw * KB, sg.small == 1 ? &maps->b_small : &maps->b_big, row, sg.b_col, &full[s]);
         if (++panel == sg.p_end) {
             ++seg;
             panel = segs[seg].p_begin;  // segs[] ends with a sentinel entry
@@ -135,9 +134,65 @@ __device__ __forceinline__ void run_segment(const Seg sg, double* ring, uint64_t
         }
 }
 
+// Diagonal 128 x 128 block of a Gram matrix, upper triangle only, perfectly balanced over the 8 warps:
+// in units of 8 x 8 DMMA blocks the triangle has 136 blocks; warp W takes block-rows W and 15 - W
+// (16 - W and W + 1 blocks: 17 each instead of 32 for a full tile).  A == B here, so the a-fragments
+// are two of the b-fragments: 16 - W shared-memory loads feed 17 DMMAs.  The eight warps run eight
+// specialised copies of the loop; one run-time-predicated copy (W a variable, 24 predicated DMMA slots)
+// was measured 30% slower.  Measured pace: that of 21 DMMAs per k-step (cost_of below).
+template <int W>
+__device__ __forceinline__ void run_segment_tri(const Seg sg, double* ring, uint64_t* full, uint64_t* empty, int& stage,
+                                                uint32_t& phase, long long& consumed, long long np_total, bool producer,
+                                                Producer& prod, double* __restrict__ part) {
+    constexpr int N0 = 16 - W, N1 = W + 1, R1 = 15 - W;   // row W: block-cols W..15; row 15-W: block-cols 15-W..15
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    double acc0[N0][2], acc1[N1][2];
+#pragma unroll
+    for (int j = 0; j < N0; ++j) acc0[j][0] = acc0[j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N1; ++j) acc1[j][0] = acc1[j][1] = 0.0;
+    for (long long p = sg.p_begin; p < sg.p_end; ++p) {
+        if (producer && consumed + PREFETCH < np_total) prod.issue(consumed + PREFETCH);
+        __syncwarp();
+        ptx::mbar_wait(&full[stage], phase);
+        const double* bp = ring + (size_t)stage * STAGE_DOUBLES + (8 * W + g) * KB + tq;
+#pragma unroll
+        for (int s = 0; s < KB / 4; ++s) {
+            double b[N0];   // fragments of block-columns W..15
+#pragma unroll
+            for (int j = 0; j < N0; ++j) b[j] = bp[j * 8 * KB + 4 * s];
+#pragma unroll
+            for (int j = 0; j < N0; ++j) ptx::dmma(acc0[j][0], acc0[j][1], b[0], b[j]);
+#pragma unroll
+            for (int j = 0; j < N1; ++j) ptx::dmma(acc1[j][0], acc1[j][1], b[R1 - W], b[R1 - W + j]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+        ++consumed;
+    }
+    double* out = part + sg.part_off;
+#pragma unroll
+    for (int j = 0; j < N0; ++j) {
+        const int r = 8 * W + g, c = 8 * (W + j) + 2 * tq;
+        out[(size_t)c * 128 + r] = acc0[j][0];
+        out[(size_t)(c + 1) * 128 + r] = acc0[j][1];
+    }
+#pragma unroll
+    for (int j = 0; j < N1; ++j) {
+        const int r = 8 * R1 + g, c = 8 * (R1 + j) + 2 * tq;
+        out[(size_t)c * 128 + r] = acc1[j][0];
+        out[(size_t)(c + 1) * 128 + r] = acc1[j][1];
+    }
+}
+
 __global__ void __launch_bounds__(256, 1)
 gemm_tn_sk_kernel(const __grid_constant__ Maps maps, const Seg* __restrict__ segs, const int* __restrict__ cta_seg,
-                  double* __restrict__ part) {
+                  double* __restrict__ part, unsigned long long* __restrict__ tlog) {
     extern __shared__ unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * STAGE_DOUBLES);
@@ -166,12 +221,27 @@ gemm_tn_sk_kernel(const __grid_constant__ Maps maps, const Seg* __restrict__ seg
     int stage = 0;
     uint32_t phase = 0;
     long long consumed = 0;
+    unsigned long long t_start = 0, t_first = 0;
+    if (tlog && threadIdx.x == 32) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     for (int s = s0; s < s1; ++s) {
         const Seg sg = segs[s];
-        if (sg.small)
+        if (tlog && threadIdx.x == 32 && s == s0 + 1) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_first));
+        if (sg.small == 1) {
             run_segment<16, 32, 64>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
-        else
+        } else if (sg.small == 2) {
+#define MOR_TRI(Wn) case Wn: run_segment_tri<Wn>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part); break;
+            switch (threadIdx.x >> 5) { MOR_TRI(0) MOR_TRI(1) MOR_TRI(2) MOR_TRI(3) MOR_TRI(4) MOR_TRI(5) MOR_TRI(6) MOR_TRI(7) }
+#undef MOR_TRI
+        } else {
             run_segment<32, 64, 128>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
+        }
+    }
+    if (tlog && threadIdx.x == 32) {   // debug: per-CTA timeline (start, end of the first segment, end), ns
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        tlog[3 * blockIdx.x] = t_start;
+        tlog[3 * blockIdx.x + 1] = t_first ? t_first : t_end;
+        tlog[3 * blockIdx.x + 2] = t_end;
     }
 }
 
@@ -179,7 +249,7 @@ __global__ void __launch_bounds__(256)
 gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const TileInfo* __restrict__ tiles, int same, int p, int q, double* __restrict__ C, int ldc,
                          int accumulate) {
     const TileInfo t = tiles[blockIdx.y];
-    const int bm = t.small ? 64 : 128;
+    const int bm = t.small == 1 ? 64 : 128;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= bm * bm) return;
     const int r = e % bm, c = e / bm;
@@ -242,25 +312,18 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         // group sweeps its rows together and shares them through L2.  mode 3 then caps every CTA at the
         // fair share Tq = total / #SMs: a primary CTA stops Tq worth of panels into its group, the cut-off
         // tails go to a pool that is handed to the CTAs with spare capacity -- the diagonal-block CTAs
-        // (three 64 x 64 tiles = 3/4 of the work of a full tile) and the SMs the classic grid leaves idle.
+        // (upper triangle only, 17/32 of the DMMAs of a full tile, see run_segment_tri) and the SMs the
+        // classic grid leaves idle.
         // mode 2 = no cap (the classic schedule run through this kernel, for A/B timing).
-        struct Prim { int tile; };
         std::vector<int> slot_tiles;                 // primary slots per group -> first tile index
         std::vector<int> slot_ntiles;                // 1 (big tile) or up to 3 (split diagonal block)
         const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
         for (int ti = 0; ti < tp; ++ti)
             for (int tj = same ? ti : 0; tj < tq_; ++tj) {
                 slot_tiles.push_back((int)tiles.size());
-                if (same && ti == tj && mode == 3) {
-                    const int c0 = ti * 128;
-                    tiles.push_back({c0, c0, 1, 1, 0, 0});
-                    int cnt = 1;
-                    if (c0 + 64 < p) {
-                        tiles.push_back({c0, c0 + 64, 1, 0, 0, 0});
-                        tiles.push_back({c0 + 64, c0 + 64, 1, 1, 0, 0});
-                        cnt = 3;
-                    }
-                    slot_ntiles.push_back(cnt);
+                if (same && ti == tj && mode == 3 && ti * 128 + 128 <= p) {
+                    tiles.push_back({ti * 128, ti * 128, 2, 1, 0, 0});   // triangular diagonal block
+                    slot_ntiles.push_back(1);
                 } else {
                     tiles.push_back({ti * 128, tj * 128, 0, (same && ti == tj) ? 1 : 0, 0, 0});
                     slot_ntiles.push_back(1);
@@ -272,9 +335,13 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         if (G > P) G = (int)std::max<long long>(1, P);
         const int nprim = G * nslots;
         if (nprim > nct) nct = nprim;                // more tiles than SMs: several waves
+        // cost per panel in DMMAs per warp per k-step; the triangular diagonal block issues 17 but was
+        // measured (per-CTA timeline, MOR_B200_SK_TLOG) at the pace of 21: 16 - W loads feed only 17 DMMAs
+        static const int tri_cost = getenv("MOR_B200_SK_TRI_COST") ? atoi(getenv("MOR_B200_SK_TRI_COST")) : 21;
+        auto cost_of = [](const TileInfo& t) { return t.small == 1 ? 8 : (t.small == 2 ? tri_cost : 32); };
         long long total = 0;
-        for (const TileInfo& t : tiles) total += (t.small ? 1 : 4) * P;
-        const long long Tq = (mode == 3) ? (total + nct - 1) / nct : (long long)4 * P + 1;
+        for (const TileInfo& t : tiles) total += cost_of(t) * P;
+        const long long Tq = (mode == 3) ? (total + nct - 1) / nct : (long long)32 * P + 1;
         struct Piece { int tile; long long a, b; };
         std::vector<std::vector<Piece>> work((size_t)nct);
         std::vector<long long> left((size_t)nct, Tq);
@@ -285,7 +352,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
                 const int c = g * nslots + sl;
                 for (int u = 0; u < slot_ntiles[sl]; ++u) {
                     const int t = slot_tiles[sl] + u;
-                    const int cost = tiles[t].small ? 1 : 4;
+                    const int cost = cost_of(tiles[t]);
                     long long take = std::min(gb - ga, left[c] / cost);
                     if (take > 0) {
                         work[c].push_back({t, ga, ga + take});
@@ -299,7 +366,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         // not needed: pieces are split freely); the last candidate takes whatever rounding leaves over
         int c = 0;
         for (Piece pc : pool) {
-            const int cost = tiles[pc.tile].small ? 1 : 4;
+            const int cost = cost_of(tiles[pc.tile]);
             int guard = 0;
             while (pc.a < pc.b) {
                 if (left[c] < (long long)cost * 4 && guard < nct) {   // too little room for a useful slice
@@ -321,7 +388,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         for (size_t t = 0; t < tiles.size(); ++t) {
             tiles[t].part_base = part_doubles;
             tiles[t].nparts = count[t];
-            part_doubles += (long long)count[t] * (tiles[t].small ? 4096 : 16384);
+            part_doubles += (long long)count[t] * (tiles[t].small == 1 ? 4096 : 16384);
             count[t] = 0;
         }
         cta_seg.clear();
@@ -330,7 +397,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
             for (const Piece& pc : work[(size_t)cc]) {
                 const TileInfo& t = tiles[(size_t)pc.tile];
                 segs.push_back({t.a_col, t.b_col, t.small, t.diag, pc.a, pc.b,
-                                t.part_base + (long long)count[(size_t)pc.tile]++ * (t.small ? 4096 : 16384)});
+                                t.part_base + (long long)count[(size_t)pc.tile]++ * (t.small == 1 ? 4096 : 16384)});
             }
         }
         cta_seg.push_back((int)segs.size());
@@ -407,8 +474,23 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         MOR_CUDA(cudaFuncSetAttribute(gemm_tn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
         attr_set = true;
     }
-    gemm_tn_sk_kernel<<<nct, 256, SK_SMEM, cx.stream>>>(maps, d_segs, d_cta, part);
+    static const bool want_tlog = getenv("MOR_B200_SK_TLOG") != nullptr;
+    DevBuf tlog;
+    if (want_tlog) MOR_TRY(tlog.alloc(sizeof(unsigned long long) * 3 * (size_t)nct));
+    gemm_tn_sk_kernel<<<nct, 256, SK_SMEM, cx.stream>>>(maps, d_segs, d_cta, part, tlog.as<unsigned long long>());
     MOR_CUDA(cudaGetLastError());
+    if (want_tlog) {
+        std::vector<unsigned long long> h(3 * (size_t)nct);
+        MOR_CUDA(cudaMemcpyAsync(h.data(), tlog.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, cx.stream));
+        MOR_CUDA(cudaStreamSynchronize(cx.stream));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < nct; ++c) t0 = std::min(t0, h[3 * (size_t)c]);
+        fprintf(stderr, "[mor_b200] gemm_tn_sk mode %d: %d CTAs, %zu segments; per CTA: nseg start first_seg_end end (ms)\n", mode, nct,
+                segs.size() - 1);
+        for (int c = 0; c < nct; ++c)
+            fprintf(stderr, "[mor_b200]   cta %3d nseg %2d  %8.3f %8.3f %8.3f\n", c, cta_seg[(size_t)c + 1] - cta_seg[(size_t)c],
+                    (h[3 * (size_t)c] - t0) * 1e-6, (h[3 * (size_t)c + 1] - t0) * 1e-6, (h[3 * (size_t)c + 2] - t0) * 1e-6);
+    }
     gemm_tn_sk_reduce_kernel<<<dim3(64, (unsigned)tiles.size()), 256, 0, cx.stream>>>(part, d_tiles, same ? 1 : 0,
                                                                                    p, q, C, ldc, accumulate);
     MOR_CUDA(cudaGetLastError());
