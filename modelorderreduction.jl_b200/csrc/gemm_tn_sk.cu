@@ -346,6 +346,16 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
         std::vector<std::vector<Piece>> work((size_t)nct);
         std::vector<long long> left((size_t)nct, Tq);
         std::vector<Piece> pool;
+        // Two-level accumulation: no register accumulator runs over more than L panels (82K rows at
+        // L = 4096) before it is flushed into its own partial tile; the partial tiles are added by the
+        // reduce kernel.  This bounds the sqrt(#terms) * eps growth of a 16M-term dot product (the
+        // known-answer run at 16M x 1024 went from 3.6e-11 to the 1e-12 level in sigma) for the price
+        // of a 128 KB store per 10 ms of DMMA work; L grows with the problem so that the partial-tile
+        // workspace stays below ~1 GB.
+        const long long L = std::max<long long>(4096, (P * (long long)tiles.size() + 8191) / 8192);
+        auto push_piece = [&](int cta_id, int tile, long long a, long long b) {
+            for (long long x = a; x < b; x += L) work[(size_t)cta_id].push_back({tile, x, std::min(b, x + L)});
+        };
         for (int g = 0; g < G; ++g) {
             const long long ga = P * g / G, gb = P * (g + 1) / G;
             for (int sl = 0; sl < nslots; ++sl) {
@@ -355,7 +365,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
                     const int cost = cost_of(tiles[t]);
                     long long take = std::min(gb - ga, left[c] / cost);
                     if (take > 0) {
-                        work[c].push_back({t, ga, ga + take});
+                        push_piece(c, t, ga, ga + take);
                         left[c] -= take * cost;
                     }
                     if (ga + take < gb) pool.push_back({t, ga + take, gb});
@@ -375,7 +385,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
                     continue;
                 }
                 const long long take = guard >= nct ? pc.b - pc.a : std::min(pc.b - pc.a, left[c] / cost);
-                work[c].push_back({pc.tile, pc.a, pc.a + take});
+                push_piece(c, pc.tile, pc.a, pc.a + take);
                 left[c] -= take * cost;
                 pc.a += take;
                 guard = 0;
