@@ -27,6 +27,11 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 Ctx& ctx() { return g_ctx; }
 
+std::recursive_mutex& api_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 int32_t require_ctx() {
     if (!g_ctx.ready) {
         // lazy default: device 0
@@ -204,6 +209,7 @@ int32_t mor_b200_version(void) { return MOR_B200_VERSION; }
 const char* mor_b200_last_error(void) { return g_last_error.c_str(); }
 
 int32_t mor_b200_init(int32_t device) {
+    MOR_API_LOCK;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (g_ctx.ready && g_ctx.device == device) return MOR_OK;
     MOR_ARG(device >= 0, "mor_b200_init: device must be >= 0");
@@ -240,6 +246,7 @@ int32_t mor_b200_init(int32_t device) {
 }
 
 int32_t mor_b200_shutdown(void) {
+    MOR_API_LOCK;
     mor_b200_comm_destroy();
     std::lock_guard<std::mutex> lock(g_mutex);
     if (g_ctx.ready) {
@@ -262,6 +269,7 @@ int32_t mor_b200_shutdown(void) {
 }
 
 int32_t mor_b200_set_stream(void* cuda_stream) {
+    MOR_API_LOCK;
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
     g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
@@ -269,18 +277,21 @@ int32_t mor_b200_set_stream(void* cuda_stream) {
 }
 
 int32_t mor_b200_sync(void) {
+    MOR_API_LOCK;
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return MOR_OK;
 }
 
 int32_t mor_b200_trim(void) {
+    MOR_API_LOCK;
     MOR_TRY(require_ctx());
     trim_pool();
     return MOR_OK;
 }
 
 int32_t mor_b200_host_alloc(uint64_t bytes, void** out) {
+    MOR_API_LOCK;
     MOR_ARG(out != nullptr, "mor_b200_host_alloc: null output pointer");
     MOR_TRY(require_ctx());
     void* p = nullptr;
@@ -294,6 +305,7 @@ int32_t mor_b200_host_alloc(uint64_t bytes, void** out) {
 }
 
 int32_t mor_b200_host_free(void* p) {
+    MOR_API_LOCK;
     if (p) MOR_CUDA(cudaFreeHost(p));
     return MOR_OK;
 }
@@ -312,6 +324,7 @@ int64_t mor_b200_launch_count(int32_t reset) {
 
 // ---- device matrices ----------------------------------------------------------------------
 int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
+    MOR_API_LOCK;
     MOR_ARG(out != nullptr && m >= 0 && n >= 0, "mor_b200_mat_alloc: bad arguments");
     MOR_TRY(require_ctx());
     int64_t ld = (m + 1) & ~int64_t(1);  // even: 16-byte aligned columns (TMA / v2 loads)
@@ -339,6 +352,7 @@ int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
 }
 
 int32_t mor_b200_mat_wrap(void* device_ptr, int64_t m, int64_t n, int64_t ld, mor_mat_t* out) {
+    MOR_API_LOCK;
     MOR_ARG(out != nullptr && device_ptr != nullptr && m >= 0 && n >= 0 && ld >= m && ld >= 1,
             "mor_b200_mat_wrap: bad arguments");
     MOR_TRY(require_ctx());
@@ -353,6 +367,7 @@ int32_t mor_b200_mat_wrap(void* device_ptr, int64_t m, int64_t n, int64_t ld, mo
 }
 
 int32_t mor_b200_mat_free(mor_mat_t a) {
+    MOR_API_LOCK;
     if (!a) return MOR_OK;
     if (a->owned && a->p) {
         if (g_ctx.ready) {
@@ -375,6 +390,7 @@ int32_t mor_b200_mat_info(mor_mat_t a, int64_t* m, int64_t* n, int64_t* ld, void
 }
 
 int32_t mor_b200_mat_upload(mor_mat_t a, const double* host, int64_t ldh) {
+    MOR_API_LOCK;
     MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_upload: bad arguments");
     MOR_TRY(require_ctx());
     if (a->m == 0 || a->n == 0) return MOR_OK;
@@ -385,6 +401,7 @@ int32_t mor_b200_mat_upload(mor_mat_t a, const double* host, int64_t ldh) {
 }
 
 int32_t mor_b200_mat_download(mor_mat_t a, double* host, int64_t ldh) {
+    MOR_API_LOCK;
     MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_download: bad arguments");
     MOR_TRY(require_ctx());
     if (a->m == 0 || a->n == 0) return MOR_OK;
@@ -396,6 +413,7 @@ int32_t mor_b200_mat_download(mor_mat_t a, double* host, int64_t ldh) {
 
 int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_row0, double param,
                        int64_t iparam) {
+    MOR_API_LOCK;
     MOR_ARG(a != nullptr && global_row0 >= 0, "mor_b200_synth: bad arguments");
     MOR_TRY(require_ctx());
     MOR_TRY(synth_fill(a->p, a->m, a->n, a->ld, kind, seed, global_row0, param, iparam));
@@ -405,6 +423,7 @@ int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_
 
 int32_t mor_b200_kat_check(mor_mat_t U, int64_t k, int64_t n, uint64_t seed, int64_t global_row0, double param,
                            double* max_err) {
+    MOR_API_LOCK;
     MOR_ARG(U != nullptr && max_err != nullptr && k >= 1 && k <= U->n && n >= k && global_row0 >= 0,
             "mor_b200_kat_check: bad arguments");
     MOR_TRY(require_ctx());

@@ -7,6 +7,7 @@ using namespace mor;
 extern "C" {
 
 int32_t mor_dbg_gemm_tn(mor_mat_t A, mor_mat_t B, mor_mat_t C) {
+    MOR_API_LOCK;
     MOR_ARG(A && B && C && A->m == B->m && C->m == A->n && C->n == B->n, "mor_dbg_gemm_tn: shapes");
     MOR_TRY(require_ctx());
     MOR_TRY(gemm_tn(A->p, A->ld, (int)A->n, B->p, B->ld, (int)B->n, A->m, C->p, (int)C->ld));
@@ -15,6 +16,7 @@ int32_t mor_dbg_gemm_tn(mor_mat_t A, mor_mat_t B, mor_mat_t C) {
 }
 
 int32_t mor_dbg_gemm_nn(mor_mat_t X, mor_mat_t W, mor_mat_t Y, int32_t upper) {
+    MOR_API_LOCK;
     MOR_ARG(X && W && Y && W->m == X->n && Y->m == X->m && Y->n == W->n, "mor_dbg_gemm_nn: shapes");
     MOR_TRY(require_ctx());
     MOR_TRY(gemm_nn(X->p, X->ld, (int)X->n, W->p, (int)W->ld, (int)W->n, X->m, Y->p, Y->ld, upper));
@@ -24,6 +26,7 @@ int32_t mor_dbg_gemm_nn(mor_mat_t X, mor_mat_t W, mor_mat_t Y, int32_t upper) {
 
 // in place: G (n x n SPD) -> R upper with R'R = G; returns the failing pivot (1-based) or 0
 int32_t mor_dbg_chol(mor_mat_t G, int32_t* fail) {
+    MOR_API_LOCK;
     MOR_ARG(G && G->m == G->n && fail, "mor_dbg_chol: shapes");
     MOR_TRY(require_ctx());
     DevBuf info;
@@ -37,6 +40,7 @@ int32_t mor_dbg_chol(mor_mat_t G, int32_t* fail) {
 }
 
 int32_t mor_dbg_trinv(mor_mat_t R, mor_mat_t Rinv) {
+    MOR_API_LOCK;
     MOR_ARG(R && Rinv && R->m == R->n && Rinv->m == R->m && Rinv->n == R->n, "mor_dbg_trinv: shapes");
     MOR_TRY(require_ctx());
     MOR_TRY(small_trinv_upper(R->p, (int)R->n, (int)R->ld, Rinv->p, (int)Rinv->ld));
@@ -45,6 +49,7 @@ int32_t mor_dbg_trinv(mor_mat_t R, mor_mat_t Rinv) {
 }
 
 int32_t mor_dbg_small_gemm(int32_t ta, int32_t tb, mor_mat_t A, mor_mat_t B, mor_mat_t C) {
+    MOR_API_LOCK;
     MOR_ARG(A && B && C, "mor_dbg_small_gemm: null");
     MOR_TRY(require_ctx());
     const int k = (int)(ta ? A->m : A->n);
@@ -56,6 +61,7 @@ int32_t mor_dbg_small_gemm(int32_t ta, int32_t tb, mor_mat_t A, mor_mat_t B, mor
 
 // in place one-sided Jacobi on A (rows x n); V (n x n) accumulated; sigma/order length n
 int32_t mor_dbg_jacobi(mor_mat_t A, mor_mat_t V, double* sigma, int32_t* order, int32_t* sweeps) {
+    MOR_API_LOCK;
     MOR_ARG(A && V && sigma && order && V->m == A->n && V->n == A->n, "mor_dbg_jacobi: shapes");
     MOR_TRY(require_ctx());
     std::vector<double> s;
@@ -116,6 +122,7 @@ extern "C" {
 // best-of-`reps` DMMA.8x8x4 issue-rate peak (TFLOP/s) and streaming read bandwidth (GB/s over
 // a `gib`-GiB buffer), measured with CUDA events on the library stream
 int32_t mor_dbg_peaks(int32_t reps, int32_t gib, double* dmma_tflops, double* read_gbs) {
+    MOR_API_LOCK;
     MOR_ARG(dmma_tflops && read_gbs && reps >= 1 && gib >= 1, "mor_dbg_peaks: bad arguments");
     MOR_TRY(require_ctx());
     Ctx& cx = ctx();

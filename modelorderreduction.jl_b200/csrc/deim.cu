@@ -281,8 +281,10 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     // L row: ell[j] = sum_{t <= j} w[t] * Z[t][j],  j < i   (Z = inv(Uf[0:i,0:i]), upper triangular)
     {
         double s = 0.0;
-        if (active && x < i)
-            for (int t = yy; t <= x; t += ways) s = fma(w[t], Z[(size_t)t * k + x], s);
+        if (active && x < i) {
+#pragma unroll 8
+            for (int t = yy; t <= x; t += ways) s = fma(w[t], __ldcg(&Z[(size_t)t * k + x]), s);
+        }
         s = combine(s);
         if (yy == 0 && x < i) {
             ell[x] = s;
@@ -294,8 +296,10 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     {
         const int j = i + x;
         double s = 0.0;
-        if (active && j < k)
-            for (int t = yy; t < i; t += ways) s = fma(ell[t], Uf[(size_t)t * k + j], s);
+        if (active && j < k) {
+#pragma unroll 8
+            for (int t = yy; t < i; t += ways) s = fma(ell[t], __ldcg(&Uf[(size_t)t * k + j]), s);
+        }
         s = combine(s);
         if (yy == 0 && j < k) Uf[(size_t)i * k + j] = w[j] - s;
     }
@@ -307,8 +311,10 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot,  r < i;  Z[i][i] = 1/pivot
     {
         double s = 0.0;
-        if (active && x < i)
-            for (int t = x + yy; t < i; t += ways) s = fma(Zt[(size_t)t * k + x], ucol[t], s);
+        if (active && x < i) {
+#pragma unroll 8
+            for (int t = x + yy; t < i; t += ways) s = fma(__ldcg(&Zt[(size_t)t * k + x]), ucol[t], s);
+        }
         s = combine(s);
         if (yy == 0 && x <= i) {
             const double z = (x == i) ? 1.0 / pivot : -s / pivot;
@@ -323,8 +329,10 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     // c = Z[0:i+1, 0:i+1] * y   (y = inv(L) * P'u_{l+1} is column i+1 of the U-factor)
     {
         double s = 0.0;
-        if (active && x <= i)
-            for (int t = x + yy; t <= i; t += ways) s = fma(Zt[(size_t)t * k + x], y[t], s);
+        if (active && x <= i) {
+#pragma unroll 8
+            for (int t = x + yy; t <= i; t += ways) s = fma(Zt[(size_t)t * k + x], y[t], s);   // row i was written above
+        }
         s = combine(s);
         if (yy == 0 && x <= i) c[x] = s;
     }
@@ -457,6 +465,7 @@ using namespace mor;
 extern "C" {
 
 int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx, mor_mat_t P_out) {
+    MOR_API_LOCK;
     MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector_dev: null argument");
     MOR_ARG(U->m == V->m && P_out->m == V->n && P_out->n == U->n, "mor_b200_deim_projector_dev: P_out must be pod_dim x deim_dim");
     MOR_TRY(require_ctx());
@@ -465,6 +474,7 @@ int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx
 
 int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp,
                                 int64_t ldv, const int64_t* idx, double* P_out, int64_t ldp) {
+    MOR_API_LOCK;
     MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector: null pointer");
     MOR_ARG(m >= 0 && kd >= 1 && kp >= 1 && ldu >= (m > 0 ? m : 1) && ldv >= (m > 0 ? m : 1) && ldp >= kp,
             "mor_b200_deim_projector: bad dimensions");
@@ -484,12 +494,14 @@ int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t 
 }
 
 int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {
+    MOR_API_LOCK;
     MOR_ARG(B != nullptr, "mor_b200_deim_indices_dev: null matrix");
     MOR_TRY(require_ctx());
     return deim_indices_device(B->p, B->m, B->n, B->ld, idx_out);
 }
 
 int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out) {
+    MOR_API_LOCK;
     MOR_ARG(B != nullptr && idx_out != nullptr, "mor_b200_deim_indices: null pointer");
     MOR_ARG(m >= 0 && k >= 1 && ldb >= (m > 0 ? m : 1), "mor_b200_deim_indices: bad dimensions");
     MOR_TRY(require_ctx());

@@ -67,6 +67,7 @@ extern "C" {
 
 int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                               const double* V, int64_t k, int64_t ldv, double* Ahat, int64_t lda) {
+    MOR_API_LOCK;
     MOR_ARG(colptr && V && Ahat && m >= 1 && k >= 1 && ldv >= m && lda >= k, "mor_b200_galerkin_csc: bad arguments");
     MOR_ARG(colptr[0] == 1 && colptr[m] >= 1, "mor_b200_galerkin_csc: colptr must be 1-based (Julia SparseMatrixCSC)");
     const int64_t nnz = colptr[m] - 1;
@@ -103,6 +104,7 @@ int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* r
 // y_hat(0) = V' snapshot[:, 1].  V and Xv are this rank's row shards; the result is replicated.
 int32_t mor_b200_project(const double* V, int64_t m, int64_t k, int64_t ldv, const double* Xv, int64_t nvec,
                          int64_t ldx, double* out, int64_t ldo) {
+    MOR_API_LOCK;
     MOR_ARG(V && Xv && out && m >= 0 && k >= 1 && nvec >= 1, "mor_b200_project: bad arguments");
     MOR_ARG(ldv >= (m > 0 ? m : 1) && ldx >= (m > 0 ? m : 1) && ldo >= k && k <= 4096 && nvec <= 4096,
             "mor_b200_project: bad dimensions");

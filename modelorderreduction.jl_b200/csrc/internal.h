@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,10 @@ struct Ctx {
 };
 Ctx& ctx();
 int32_t require_ctx();
+// Every public entry point holds this (recursive: entry points call each other) for its duration:
+// calls from several host threads are safe and simply serialise on the one per-process context.
+std::recursive_mutex& api_mutex();
+#define MOR_API_LOCK std::lock_guard<std::recursive_mutex> api_lock__(::mor::api_mutex())
 inline void count_launch(int n = 1) { ctx().launches += n; }
 // Grow-only device workspace of at least `bytes`; contents are only valid until the next
 // scratch() call on this context (all users are ordered on ctx().stream).

@@ -119,6 +119,7 @@ using namespace mor;
 extern "C" {
 
 int32_t mor_b200_comm_unique_id(void* id128) {
+    MOR_API_LOCK;
     MOR_ARG(id128 != nullptr, "mor_b200_comm_unique_id: null buffer");
     MOR_TRY(load_nccl());
     ncclUniqueId id;
@@ -129,6 +130,7 @@ int32_t mor_b200_comm_unique_id(void* id128) {
 }
 
 int32_t mor_b200_comm_init(int32_t rank, int32_t nranks, const void* id128) {
+    MOR_API_LOCK;
     MOR_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "mor_b200_comm_init: bad rank/nranks");
     MOR_TRY(require_ctx());
     Ctx& c = ctx();
@@ -158,6 +160,7 @@ int32_t mor_b200_comm_info(int32_t* rank, int32_t* nranks) {
 }
 
 int32_t mor_b200_comm_destroy(void) {
+    MOR_API_LOCK;
     Ctx& c = ctx();
     if (c.comm && g_nccl.CommDestroy) {
         if (c.ready) {

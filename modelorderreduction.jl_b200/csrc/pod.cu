@@ -524,6 +524,7 @@ extern "C" {
 
 int32_t mor_b200_pod_factor_dev(mor_mat_t X, int32_t method, int64_t k, int64_t p, mor_mat_t Omega, uint64_t seed,
                                 int32_t flags, mor_pod_t* handle, double* S_out, int64_t* nS) {
+    MOR_API_LOCK;
     MOR_ARG(X != nullptr, "mor_b200_pod_factor_dev: null matrix");
     MOR_TRY(require_ctx());
     MOR_ARG(X->ld % 2 == 0 && (uintptr_t)X->p % 16 == 0,
@@ -620,17 +621,20 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
 
 int32_t mor_b200_pod_factor(const double* X, int64_t m, int64_t n, int64_t ldx, int32_t method, int64_t k, int64_t p,
                             const double* Omega, uint64_t seed, mor_pod_t* handle, double* S_out, int64_t* nS) {
+    MOR_API_LOCK;
     return factor_from_host(X, nullptr, m, n, ldx, method, k, p, Omega, seed, handle, S_out, nS);
 }
 
 int32_t mor_b200_pod_factor_cols(const double* const* cols, int64_t m, int64_t n, int32_t method, int64_t k,
                                  int64_t p, const double* Omega, uint64_t seed, mor_pod_t* handle, double* S_out,
                                  int64_t* nS) {
+    MOR_API_LOCK;
     MOR_ARG(cols != nullptr, "mor_b200_pod_factor_cols: null pointer");
     return factor_from_host(nullptr, cols, m, n, m, method, k, p, Omega, seed, handle, S_out, nS);
 }
 
 int32_t mor_b200_pod_basis_dev(mor_pod_t h, int64_t k, mor_mat_t U_out) {
+    MOR_API_LOCK;
     MOR_ARG(h != nullptr && U_out != nullptr, "mor_b200_pod_basis_dev: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_basis_dev: k must be in 1..number of computed triplets");
     MOR_ARG(U_out->m == h->m && U_out->n >= k, "mor_b200_pod_basis_dev: U_out must be m x >= k");
@@ -653,6 +657,7 @@ int32_t mor_b200_pod_basis_dev(mor_pod_t h, int64_t k, mor_mat_t U_out) {
 }
 
 int32_t mor_b200_pod_right_dev(mor_pod_t h, int64_t k, mor_mat_t V_out) {
+    MOR_API_LOCK;
     MOR_ARG(h != nullptr && V_out != nullptr, "mor_b200_pod_right_dev: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_right_dev: k must be in 1..number of computed triplets");
     MOR_ARG(V_out->m == h->n && V_out->n >= k, "mor_b200_pod_right_dev: V_out must be n x >= k");
@@ -673,6 +678,7 @@ int32_t mor_b200_pod_right_dev(mor_pod_t h, int64_t k, mor_mat_t V_out) {
 }
 
 int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, double* V_out, int64_t ldv) {
+    MOR_API_LOCK;
     MOR_ARG(h != nullptr && U_out != nullptr, "mor_b200_pod_basis: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_basis: k must be in 1..number of computed triplets");
     MOR_ARG(ldu >= std::max<int64_t>(h->m, 1) && (!V_out || ldv >= h->n), "mor_b200_pod_basis: leading dimension too small");
@@ -711,6 +717,7 @@ int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, d
 }
 
 int32_t mor_b200_pod_free(mor_pod_t h) {
+    MOR_API_LOCK;
     if (!h) return MOR_OK;
     if (ctx().ready) {
         cudaSetDevice(ctx().device);
@@ -728,6 +735,7 @@ int32_t mor_b200_pod_info(mor_pod_t h, int32_t* passes, int32_t* sweeps) {
 }
 
 int32_t mor_b200_orthonormalize_dev(mor_mat_t A, int32_t* passes) {
+    MOR_API_LOCK;
     MOR_ARG(A != nullptr, "mor_b200_orthonormalize_dev: null matrix");
     MOR_TRY(require_ctx());
     MOR_ARG(A->n >= 1 && A->n <= 4096, "mor_b200_orthonormalize_dev: column count must be in 1..4096");

@@ -139,3 +139,26 @@ def test_galerkin_projection_of_the_linear_part(gpu):
     assert np.max(np.abs(y0 - pod.rbasis.T @ X[:, 0])) <= 1e-13 * max(np.linalg.norm(X[:, 0]), 1.0)
     with pytest.raises(ValueError):
         mor_b200.galerkin_project(sp.eye(7, format="csc"), np.ones((8, 2)))
+
+
+def test_calls_from_several_host_threads_serialise(gpu):
+    """The library is one context per process; concurrent calls from several host threads (ctypes
+    drops the GIL, like Julia tasks on several threads) must serialise on it and all be correct."""
+    import threading
+    rng = np.random.Generator(np.random.PCG64(3))
+    mats = [np.asfortranarray(np.linalg.qr(rng.standard_normal((20_000 + 37 * i, 12 + i)))[0]) for i in range(6)]
+    want = [O.deim_interpolation_indices(Q).tolist() for Q in mats]
+    got = [None] * len(mats)
+    pods = [None] * len(mats)
+
+    def work(i):
+        got[i] = mor_b200.deim_interpolation_indices(mats[i]).tolist()
+        p = mor_b200.POD(mats[i], 3)
+        mor_b200.reduce(p, mor_b200.SVD())
+        pods[i] = p.spectrum
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(mats))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert got == want
+    for s in pods:                      # orthonormal columns: all singular values are 1
+        assert np.max(np.abs(s - 1.0)) < 1e-12
