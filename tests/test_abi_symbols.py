@@ -55,3 +55,32 @@ def test_no_cpu_fallback_without_device():
     import mor_b200
     with pytest.raises(_lib.MorError):
         mor_b200.deim_interpolation_indices(B)
+
+
+def _build_c_consumer(tmp_path):
+    import subprocess
+    libdir = os.path.join(ROOT, "modelorderreduction.jl_b200", "lib")
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L" + libdir, "-lmor_b200",
+                    "-Wl,-rpath," + libdir, "-lm"], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/mor_b200.h compiles as strict C99 and a plain-C program links against the library;
+    without a device it gets MOR_ERR_CUDA from the compute entry points (exit code 3)."""
+    import subprocess
+    exe = _build_c_consumer(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode in (0, 3), out.stdout + out.stderr
+    if out.returncode == 3:
+        assert "no CUDA device" in out.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_on_gpu(tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_consumer(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c_abi_smoke ok" in out.stdout
