@@ -212,6 +212,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks_ok(flag):
+        """True only if `flag` is true on every rank (keeps the ranks in step when an optional
+        section cannot run on one of them, e.g. a pinned allocation fails)."""
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
     def sum_over_ranks(x):
         if world == 1:
             return x
@@ -319,10 +328,16 @@ def run_ours(args):
         if need_gb * 1.15 + 8 > avail:
             e2e = {"value": None, "unit": "TFLOP/s", "skipped": f"host shard needs {need_gb:.0f} GB pinned, "
                    f"{avail:.0f} GB available per rank"}
-        else:
-            Xh, Uh = C.c_void_p(), C.c_void_p()     # pinned, column-major m_loc x n and m_loc x k
-            _lib.check(lib.mor_b200_host_alloc(m_loc * n * 8, C.byref(Xh)))
-            _lib.check(lib.mor_b200_host_alloc(m_loc * k * 8, C.byref(Uh)))
+        Xh, Uh = C.c_void_p(), C.c_void_p()     # pinned, column-major m_loc x n and m_loc x k
+        if e2e is None:
+            got = (lib.mor_b200_host_alloc(m_loc * n * 8, C.byref(Xh)) == _lib.OK and
+                   lib.mor_b200_host_alloc(m_loc * k * 8, C.byref(Uh)) == _lib.OK)
+            if not all_ranks_ok(got):
+                lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
+                e2e = {"value": None, "unit": "TFLOP/s", "skipped": "pinned host allocation failed on at least one rank"}
+        elif world > 1:
+            all_ranks_ok(False)                 # keep the collective sequence identical on every rank
+        if e2e is None:
             _lib.check(lib.mor_b200_mat_download(X.handle, Xh, max(m_loc, 1)))
             X.free(); U.free()
             S = np.empty(n); nS = C.c_int64(0)
@@ -422,9 +437,15 @@ def run_ours(args):
     deim_step_ms = max_over_ranks(dacc["deim_step"] / args.steps)
     # DEIM through the host-pointer entry point (what the Julia shim calls), pinned host basis
     deim_e2e = None
-    if not args.no_e2e and md_loc * kd * 8 / 1e9 * 1.15 + 8 < mem_available_gb() / max(1, min(world, 8)):
-        Bh = C.c_void_p()
-        _lib.check(lib.mor_b200_host_alloc(md_loc * kd * 8, C.byref(Bh)))
+    Bh = C.c_void_p()
+    deim_e2e_ok = False
+    if not args.no_e2e:
+        fits = md_loc * kd * 8 / 1e9 * 1.15 + 8 < mem_available_gb() / max(1, min(world, 8))
+        got = fits and lib.mor_b200_host_alloc(md_loc * kd * 8, C.byref(Bh)) == _lib.OK
+        deim_e2e_ok = all_ranks_ok(got)
+        if not deim_e2e_ok:
+            lib.mor_b200_host_free(Bh)
+    if deim_e2e_ok:
         _lib.check(lib.mor_b200_mat_download(B.handle, Bh, max(md_loc, 1)))
         idx_h = np.empty(kd, dtype=np.int64)
         for it in range(args.e2e_warmup + args.e2e_steps):
