@@ -230,7 +230,10 @@ gemm_tn_sk_kernel(const __grid_constant__ Maps maps, const Seg* __restrict__ seg
             run_segment<16, 32, 64>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
         } else if (sg.small == 2) {
 #define MOR_TRI(Wn) case Wn: run_segment_tri<Wn>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part); break;
-            switch (threadIdx.x >> 5) { MOR_TRI(0) MOR_TRI(1) MOR_TRI(2) MOR_TRI(3) MOR_TRI(4) MOR_TRI(5) MOR_TRI(6) MOR_TRI(7) }
+            // logical row pair W for physical warp w: the two warps that share an SM sub-partition
+            // (w and w + 4) get pairs W and 7 - W, i.e. 16 - W and 9 + W fragment loads: 25 on every SMSP
+            const int wphys = threadIdx.x >> 5;
+            switch (wphys < 4 ? wphys : 11 - wphys) { MOR_TRI(0) MOR_TRI(1) MOR_TRI(2) MOR_TRI(3) MOR_TRI(4) MOR_TRI(5) MOR_TRI(6) MOR_TRI(7) }
 #undef MOR_TRI
         } else {
             run_segment<32, 64, 128>(sg, ring, full, empty, stage, phase, consumed, np_total, producer, prod, part);
