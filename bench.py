@@ -166,7 +166,7 @@ def workload_config(args, world):
     m = args.rows
     cfg = {"workload": f"POD reduce!(pod, SVD()) of a synthetic {m}x{N_COLS} FP64 snapshot matrix (N(0,1) entries, "
                        f"column scale 10^(-3j/(n-1)), Philox seed 3), nmodes={K_MODES}; "
-                       f"DEIM on a {args.deim_rows}x{DEIM_K} orthonormal basis",
+                       f"DEIM on the {args.deim_rows}x{DEIM_K} POD basis of 2-D Burgers snapshots",
            "m": m, "n": N_COLS, "k": K_MODES, "parallelism": f"rows/{world}",
            "l2": "inputs (>= 17 GB per GPU) are larger than the 126 MB L2; no flush needed"}
     if m != M_FULL:
@@ -419,9 +419,40 @@ def run_ours(args):
     # ---- DEIM: 16M x 256 orthonormal basis, row-sharded ------------------------------------------
     Md, kd = args.deim_rows, DEIM_K
     r0d, md_loc = mdist.shard_rows(Md, world, rank)
-    B = DeviceMatrix.alloc(md_loc, kd).synth(_lib.SYNTH_GAUSS, seed=5, global_row0=r0d, param=1.0 / math.sqrt(Md))
-    orth_passes = orthonormalize_dev(B)
-    dacc = {"deim_step": 0.0, "deim_tail": 0.0, "comm": 0.0}
+    # control basis (data-independent timing check): Philox Gaussian orthonormalised by the library, 1 + 2 runs
+    Bc = DeviceMatrix.alloc(md_loc, kd).synth(_lib.SYNTH_GAUSS, seed=5, global_row0=r0d, param=1.0 / math.sqrt(Md))
+    orth_passes = orthonormalize_dev(Bc)
+    deim_indices_dev(Bc)
+    barrier()
+    e0.record(stream)
+    for _ in range(2):
+        idx_c = deim_indices_dev(Bc)
+    e1.record(stream)
+    barrier()
+    control_ms = max_over_ranks(e0.elapsed_time(e1) / 2)
+    Bc.free()
+    # the named basis (BASELINE config 5): 2-D viscous Burgers snapshots on a 4096-wide grid (Cole-Hopf closed
+    # form, u component, 256 times), POD'd by this library to 256 orthonormal columns
+    nxb = 4096 if Md >= 4096 * 4096 else max(1, int(math.isqrt(Md)))
+    Sb = DeviceMatrix.alloc(md_loc, kd).synth(_lib.SYNTH_BURGERS, seed=5, global_row0=r0d, param=args.burgers_nu, iparam=nxb)
+    B = DeviceMatrix.alloc(md_loc, kd)
+    barrier()
+    t0 = time.perf_counter()
+    fb = pod_factor_dev(Sb, _lib.MOR_SVD, kd, flags=_lib.POD_MAY_OVERWRITE, m_global=Md)
+    fb.basis(kd, B)
+    barrier()
+    basis_pod_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    BtB = DeviceMatrix.alloc(kd, kd)
+    _lib.check(lib.mor_dbg_gemm_tn(B.handle, B.handle, BtB.handle))
+    gb = torch.from_numpy(np.ascontiguousarray(BtB.to_host())).cuda()
+    if world > 1:
+        dist.all_reduce(gb)
+    burgers = {"grid": f"{nxb} x {-(-Md // nxb)}", "viscosity": args.burgers_nu, "snapshots": kd,
+               "pod_ms": basis_pod_ms, "cholqr_passes": fb.info()[0], "jacobi_sweeps": fb.info()[1],
+               "sigma_head": [float(v) for v in fb.s[:3]], "sigma_last_over_first": float(fb.s[-1] / fb.s[0]),
+               "basis_orthonormality_max_abs": float((gb - torch.eye(kd, dtype=torch.float64, device="cuda")).abs().max().item())}
+    fb.free(); Sb.free(); BtB.free()
+    dacc = {"deim_step": 0.0, "deim_tail": 0.0, "deim_panel": 0.0, "comm": 0.0}
     for _ in range(args.warmup):
         idx = deim_indices_dev(B)
     barrier()
@@ -433,8 +464,27 @@ def run_ours(args):
             dacc[s_] += t[s_]
     e1.record(stream)
     barrier()
+    deim_blocked = bool(_lib.last_timings()["deim_blocked"])
     deim_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     deim_step_ms = max_over_ranks(dacc["deim_step"] / args.steps)
+    deim_panel_ms = max_over_ranks(dacc["deim_panel"] / args.steps)
+    # the same indices by the streaming path (one pass over columns 1..l per greedy step: the reference's own
+    # access pattern and the kernel the HBM roofline of north_star is stated for): 1 warm-up + 2 timed
+    os.environ["MOR_B200_DEIM_BLOCK"] = "0"
+    sacc = {"deim_step": 0.0, "deim_tail": 0.0}
+    idx_s = deim_indices_dev(B)
+    barrier()
+    e0.record(stream)
+    for _ in range(2):
+        idx_s = deim_indices_dev(B)
+        t = _lib.last_timings()
+        for s_ in sacc:
+            sacc[s_] += t[s_]
+    e1.record(stream)
+    barrier()
+    del os.environ["MOR_B200_DEIM_BLOCK"]
+    stream_ms = max_over_ranks(e0.elapsed_time(e1) / 2)
+    stream_step_ms = max_over_ranks(sacc["deim_step"] / 2)
     # DEIM through the host-pointer entry point (what the Julia shim calls), pinned host basis
     deim_e2e = None
     Bh = C.c_void_p()
@@ -461,17 +511,45 @@ def run_ours(args):
                     "api": "mor_b200_deim_indices (host pointers, pinned)"}
         lib.mor_b200_host_free(Bh)
     deim_gbs = deim_bytes(Md, kd) / (deim_ms * 1e-3) * 1e-9
+    # traffic model of the blocked path, per rank: panel kernels read l0 + bw columns and write bw (l0 = 16, 32, ..),
+    # the greedy steps inside a block read j + 1 panel columns (j = 0 .. bw-1)
+    blocks = [(l0, min(16, kd - l0)) for l0 in range(0, kd, 16)]
+    panel_bytes = 8.0 * md_loc * sum(l0 + 2 * bw for l0, bw in blocks if l0 > 0)
+    inblock_bytes = 8.0 * md_loc * sum(bw * (bw + 1) // 2 for _, bw in blocks)
+    stream_roof = {"bound": "hbm", "kernel": "deim_step_kernel (all k launches, streaming path)",
+                   "achieved": deim_bytes(Md, kd) / world / (stream_step_ms * 1e-3) * 1e-9,
+                   "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                   "frac": deim_bytes(Md, kd) / world / (stream_step_ms * 1e-3) * 1e-9 / hbm_peak,
+                   "live_read_peak_gbs": pk_g.value,
+                   # ncu --set full of greedy step 201 at 4,194,304 rows: 6.7504 GB read+written for
+                   # 6.7444 GB algorithmic (profiles/r01_ncu_summary.txt): 1.001 x, summed over the k launches
+                   "traffic": 1.001 * deim_bytes(Md, kd) / world,
+                   "traffic_note": "ncu-measured 1.001 x algorithmic bytes (one launch), applied to all k launches"}
+    if deim_blocked:
+        roof = {"bound": "hbm", "kernel": "deim_panel_kernel (one launch per 16 columns; DMMA, TMA bulk ring)",
+                "achieved": panel_bytes / (deim_panel_ms * 1e-3) * 1e-9 if deim_panel_ms > 0 else None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                "frac": panel_bytes / (deim_panel_ms * 1e-3) * 1e-9 / hbm_peak if deim_panel_ms > 0 else None,
+                "live_read_peak_gbs": pk_g.value, "traffic": None,
+                "bytes_per_rank": panel_bytes, "kernel_ms": deim_panel_ms,
+                "in_block_steps": {"kernel": "deim_step_kernel on the 16-column residual panel (k launches)",
+                                   "bytes_per_rank": inblock_bytes, "kernel_ms": deim_step_ms,
+                                   "achieved": inblock_bytes / (deim_step_ms * 1e-3) * 1e-9,
+                                   "frac": inblock_bytes / (deim_step_ms * 1e-3) * 1e-9 / hbm_peak}}
+    else:
+        roof = stream_roof
     deim = {"ms": deim_ms, "algorithmic_gbs": deim_gbs, "m": Md, "k": kd, "distinct_indices": len(set(idx.tolist())),
-            "basis": f"Philox Gaussian orthonormalised by the library's CholeskyQR ({orth_passes} passes)",
-            "roofline": {"bound": "hbm", "kernel": "deim_step_kernel (all k launches)",
-                         "achieved": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9,
-                         "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
-                         "frac": deim_bytes(Md, kd) / world / (deim_step_ms * 1e-3) * 1e-9 / hbm_peak,
-                         "live_read_peak_gbs": pk_g.value,
-                         # ncu --set full of greedy step 201 at 4,194,304 rows: 6.7504 GB read+written for
-                         # 6.7444 GB algorithmic (profiles/r01_ncu_summary.txt): 1.001 x, summed over the k launches
-                         "traffic": 1.001 * deim_bytes(Md, kd) / world,
-                         "traffic_note": "ncu-measured 1.001 x algorithmic bytes (one launch), applied to all k launches"},
+            "path": "blocked (16-column residual panels)" if deim_blocked else "streaming",
+            "algorithmic_gbs_note": "reference-formulation bytes 4 m k (k+1) / time; the blocked path moves "
+                                    f"{(panel_bytes + inblock_bytes) * world / deim_bytes(Md, kd):.3f} x of them, so this "
+                                    "figure may exceed the HBM peak",
+            "basis": "POD basis (this library, SVD(), k=256) of 2-D viscous Burgers snapshots, Cole-Hopf closed form "
+                     "(MOR_SYNTH_BURGERS)", "burgers": burgers, "index_range": [int(idx.min()), int(idx.max())],
+            "control": {"basis": f"Philox Gaussian orthonormalised by the library's CholeskyQR ({orth_passes} passes)",
+                        "ms": control_ms, "distinct_indices": len(set(idx_c.tolist()))},
+            "roofline": roof,
+            "streaming": {"ms": stream_ms, "algorithmic_gbs": deim_bytes(Md, kd) / (stream_ms * 1e-3) * 1e-9,
+                          "same_indices_as_blocked": bool(np.array_equal(idx_s, idx)), "roofline": stream_roof},
             "tail_ms": dacc["deim_tail"] / args.steps, "e2e": deim_e2e}
     B.free()
     if world > 1:
@@ -540,6 +618,7 @@ def main():
     ap.add_argument("--no-kat", action="store_true")
     ap.add_argument("--rsvd-rows-per-gpu", type=int, default=8 * 2**20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--burgers-nu", type=float, default=2.5e-4, help="viscosity of the config-5 Burgers snapshots")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,6 +54,9 @@ extern "C" {
 #define MOR_SYNTH_KAT 3     /* known-answer matrix H_u [S V'; 0]: singular values exactly 10^(-param j/(n-1)),
                                left vectors the columns of the Householder reflector H_u.  COLLECTIVE over
                                the ranks (one all-reduce); every rank passes its own global_row0            */
+#define MOR_SYNTH_BURGERS 4 /* u component of a 2-D viscous Burgers solution (Cole-Hopf closed form: three states,
+                               travelling fronts merging in a triple point) on a grid `iparam` nodes wide, row =
+                               ix + iparam * iy, column j = time j/(n-1), viscosity `param` (BASELINE config 5) */
 
 typedef struct mor_pod_s* mor_pod_t; /* factorisation handle (owns device memory)  */
 typedef struct mor_mat_s* mor_mat_t; /* device-resident column-major FP64 matrix   */
@@ -181,6 +184,8 @@ int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx
 #define MOR_T_DEIM_TAIL 8 /* sum of the per-step small kernels                     */
 #define MOR_T_D2H 9
 #define MOR_T_SKETCH 10   /* RSVD: Y = X*Omega and B = Q'X                        */
+#define MOR_T_DEIM_PANEL 11 /* DEIM blocked path: panel residual kernels (one per 16 columns) */
+#define MOR_T_DEIM_BLOCKED 12 /* not a time: 1 if the last DEIM call took the blocked path, else 0 */
 #define MOR_T_NSLOTS 16
 int32_t mor_b200_last_timings(double* ms, int32_t n);
 /* number of kernel launches issued by the library since the last reset (this rank) */

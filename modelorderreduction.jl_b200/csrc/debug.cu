@@ -6,6 +6,26 @@ using namespace mor;
 
 extern "C" {
 
+// R (m x bw) = U[:, l0 : l0+bw] - U[:, 0 : l0] * Cm  (Cm: l0 x bw on the device) through deim_panel_kernel
+int32_t mor_dbg_deim_panel(mor_mat_t U, int32_t l0, int32_t bw, mor_mat_t Cm, mor_mat_t R) {
+    MOR_API_LOCK;
+    MOR_ARG(U && Cm && R && l0 >= 16 && l0 % 16 == 0 && bw >= 1 && bw <= 16 && U->n >= l0 + bw && Cm->m == l0 &&
+                Cm->n == bw && R->m == U->m && R->n >= bw,
+            "mor_dbg_deim_panel: shapes");
+    MOR_TRY(require_ctx());
+    std::vector<double> ch((size_t)Cm->ld * bw), cp((size_t)(l0 / 16) * 320, 0.0);
+    MOR_CUDA(cudaMemcpy(ch.data(), Cm->p, sizeof(double) * ch.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < l0 / 16; ++c)
+        for (int q = 0; q < bw; ++q)
+            for (int kk = 0; kk < 16; ++kk) cp[(size_t)c * 320 + q * 20 + kk] = ch[(size_t)q * Cm->ld + 16 * c + kk];
+    DevBuf d;
+    MOR_TRY(d.alloc(sizeof(double) * cp.size()));
+    MOR_CUDA(cudaMemcpyAsync(d.p, cp.data(), sizeof(double) * cp.size(), cudaMemcpyHostToDevice, ctx().stream));
+    MOR_TRY(deim_panel(U->p, U->ld, l0, bw, d.as<double>(), U->m, R->p, R->ld));
+    MOR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return MOR_OK;
+}
+
 int32_t mor_dbg_gemm_tn(mor_mat_t A, mor_mat_t B, mor_mat_t C) {
     MOR_API_LOCK;
     MOR_ARG(A && B && C && A->m == B->m && C->m == A->n && C->n == B->n, "mor_dbg_gemm_tn: shapes");

@@ -17,6 +17,7 @@
 // dot product instead of a 255-long dependent substitution chain.
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -87,6 +88,7 @@ __device__ __forceinline__ void cand_take(double& bv, long long& bi, double v, l
 }
 
 constexpr int DEIM_THREADS = 256;
+constexpr int DEIM_BLOCK = 16;   // panel width of the blocked path (= the 16-column stages of deim_panel_kernel)
 
 // Fused residual + abs-argmax over this rank's rows.  l = number of previous columns.
 // VEC: 16-byte loads (needs 16B-aligned base and even ld).  Each CTA walks chunks of
@@ -190,9 +192,11 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
 
 // Reduce the per-CTA candidates of this rank and gather the winner's basis row:
 // send = [value, bits(global index), U[idx, 0..k)]
+// (blocked path: followed by the winner's row of the current residual panel, Pn[idx, 0..bw), padded to 16)
 __global__ void __launch_bounds__(1024)
 deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __restrict__ U, int64_t ld,
-                  int64_t row_offset, int k, double* __restrict__ send) {
+                  int64_t row_offset, int k, double* __restrict__ send, const double* __restrict__ Pn,
+                  int64_t ldp, int bw) {
     __shared__ double sv[32];
     __shared__ long long si[32];
     __shared__ long long widx;
@@ -216,6 +220,9 @@ deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __res
     const long long g = widx;
     for (int j = threadIdx.x; j < k; j += 1024)
         send[2 + j] = (g == MOR_IDX_NONE) ? 0.0 : U[(g - row_offset) + (int64_t)j * ld];
+    if (Pn != nullptr && threadIdx.x < DEIM_BLOCK)
+        send[2 + k + threadIdx.x] =
+            (g == MOR_IDX_NONE || (int)threadIdx.x >= bw) ? 0.0 : Pn[(g - row_offset) + (int64_t)threadIdx.x * ldp];
 }
 
 __device__ __forceinline__ double warp_sum(double s) {
@@ -231,11 +238,28 @@ __device__ __forceinline__ double warp_sum(double s) {
 // Every phase is a (triangular) matrix-vector product: thread (x, y) accumulates the terms
 // t = y (mod ways) of output x, the `ways` partial sums are combined through shared memory --
 // a sequential depth of k / ways instead of k on this latency-critical single-CTA kernel.
+struct UpdState {
+    double *Wm, *Uf, *Lm, *Z, *Zt, *c;   // k x k row-major (stride k) factors and the next coefficient vector
+    long long* idx_out;                  // selected indices (1-based) or nullptr
+    int i, k;                            // step (row being appended) and dimension of this state
+    int rowoff;                          // offset of this state's row inside a gathered record
+    int last;                            // 1: the final greedy step (a zero pivot no longer matters)
+};
+struct UpdArgs {
+    UpdState st[2];                      // blockIdx.x selects: 0 = P'U of the basis, 1 = P'R of the current panel
+};
+
 __global__ void __launch_bounds__(1024)
-deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k, double* __restrict__ Wm,
-                   double* __restrict__ Uf, double* __restrict__ Lm, double* __restrict__ Z,
-                   double* __restrict__ Zt, double* __restrict__ c, long long* __restrict__ idx_out,
-                   int* __restrict__ status) {
+deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, UpdArgs args, int* __restrict__ status) {
+    const UpdState& S = args.st[blockIdx.x];
+    const int i = S.i, k = S.k;
+    double* __restrict__ Wm = S.Wm;
+    double* __restrict__ Uf = S.Uf;
+    double* __restrict__ Lm = S.Lm;
+    double* __restrict__ Z = S.Z;
+    double* __restrict__ Zt = S.Zt;
+    double* __restrict__ c = S.c;
+    long long* __restrict__ idx_out = S.idx_out;
     __shared__ double w[1024], ell[1024], ucol[1024], y[1024], part[1024];
     __shared__ int win_s;
     const int tid = threadIdx.x;
@@ -243,7 +267,6 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     const int ways = 1024 / KP;          // reduction split (k <= 1024 => ways >= 1)
     const int x = tid % KP, yy = tid / KP;
     const bool active = yy < ways;
-    const int stride = k + 2;
     if (tid == 0) {
         int win = 0;
         double bv = -1.0;
@@ -258,10 +281,10 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
             }
         }
         win_s = win;
-        idx_out[i] = bi + 1;  // 1-based, like Julia
+        if (idx_out != nullptr) idx_out[i] = bi + 1;  // 1-based, like Julia
     }
     __syncthreads();
-    const double* src = gathered + (size_t)win_s * stride + 2;
+    const double* src = gathered + (size_t)win_s * stride + S.rowoff;
     for (int j = tid; j < k; j += 1024) {
         const double v = src[j];
         w[j] = v;
@@ -307,7 +330,7 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     for (int t = tid; t < i; t += 1024) ucol[t] = Uf[(size_t)t * k + i];
     __syncthreads();
     const double pivot = Uf[(size_t)i * k + i];
-    if (tid == 0 && pivot == 0.0 && i < k - 1 && *status == 0) *status = i + 1;
+    if (tid == 0 && pivot == 0.0 && !S.last && idx_out != nullptr && *status == 0) *status = i + 1;
     // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot,  r < i;  Z[i][i] = 1/pivot
     {
         double s = 0.0;
@@ -338,6 +361,35 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int i, int k
     }
 }
 
+// Coefficients of the next panel, packed for deim_panel_kernel: C = Z[0:l1, 0:l1] * Uf[0:l1, l1 : l1+bw]
+// (Uf[:, j] = inv(L) P'u_j is already part of the U-factor, Z = inv(Uf[0:l1, 0:l1])), i.e. column q of C
+// solves (P'U_l1) c = P'u_{l1+q}, deim.jl:21.  One CTA per 16-row slab: Cp[c][q][kk] = C[16 c + kk][q].
+__global__ void __launch_bounds__(DEIM_BLOCK * 20)
+deim_block_coef_kernel(const double* __restrict__ Z, const double* __restrict__ Uf, int k, int l1, int bw,
+                       double* __restrict__ Cp) {
+    const int e = threadIdx.x, q = e / 20, kk = e % 20;
+    const int t = blockIdx.x * DEIM_BLOCK + kk;
+    double s0 = 0.0, s1 = 0.0;
+    if (kk < DEIM_BLOCK && q < bw && t < l1) {
+        const double* z = Z + (size_t)t * k;
+        const double* u = Uf + l1 + q;
+        int r = t;
+        for (; r + 2 <= l1; r += 2) {
+            s0 = fma(z[r], u[(size_t)r * k], s0);
+            s1 = fma(z[r + 1], u[(size_t)(r + 1) * k], s1);
+        }
+        if (r < l1) s0 = fma(z[r], u[(size_t)r * k], s0);
+    }
+    Cp[(size_t)blockIdx.x * (DEIM_BLOCK * 20) + e] = s0 + s1;
+}
+
+// MOR_B200_DEIM_BLOCK=0 selects the streaming path (one pass over columns 1..l per greedy step, the
+// reference's own access pattern); default is the blocked path whenever the basis layout allows it.
+static bool deim_blocked_enabled() {
+    const char* e = getenv("MOR_B200_DEIM_BLOCK");
+    return !(e && e[0] == '0');
+}
+
 int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host) {
     Ctx& cx = ctx();
     MOR_ARG(B != nullptr && idx_host != nullptr, "deim_interpolation_indices: null pointer");
@@ -361,12 +413,34 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     if (grid < 1) grid = 1;
     const bool vec = ((uintptr_t)B % 16 == 0) && (ld % 2 == 0);
 
+    // Blocked path (k > 16): the residuals of 16 columns at a time with respect to all earlier points come
+    // from ONE pass over the earlier columns (deim_panel_kernel); the greedy steps inside a block run the
+    // same streaming kernel on that 16-column residual panel -- about 8 m k (k / 32 + 18) bytes of traffic
+    // instead of 4 m k (k + 1).  It needs a 16-byte aligned basis with an even leading dimension (bulk
+    // copies) and 128 m bytes of workspace; every rank must take the same path (the gathered records differ).
+    const int64_t ldp = (m + 1) & ~int64_t(1);
+    bool blocked = deim_blocked_enabled() && k > DEIM_BLOCK && (m == 0 || (vec && ld >= ldp));
+    DevBuf panel;
+    if (blocked && m > 0 && panel.alloc(sizeof(double) * (size_t)ldp * DEIM_BLOCK) != MOR_OK) {
+        cudaGetLastError();   // no room for the panel: the streaming path needs no workspace
+        blocked = false;
+    }
+    if (cx.nranks > 1) {   // all ranks or none
+        std::vector<int64_t> votes;
+        MOR_TRY(comm_allgather_i64(blocked ? 1 : 0, votes));
+        for (int64_t v : votes) blocked = blocked && v != 0;
+        if (!blocked) panel.release();
+    }
+
     const size_t kk = (size_t)k * k;
+    const int rec = (int)k + 2 + (blocked ? DEIM_BLOCK : 0);   // gathered record: value, index, basis row, panel row
     DevBuf state, cands, xfer;
-    // state: Wm, Uf, Lm, Z, Zt (k*k each), c (k), idx (k int64), status
-    MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k) + sizeof(long long) * k + 16));
+    // state: Wm, Uf, Lm, Z, Zt (k*k each), c (k), idx (k int64), status; block state: 5 * 16*16 + 16; packed C
+    const size_t bdoubles = 5 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK;
+    const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
+    MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k + bdoubles + cp_doubles) + sizeof(long long) * k + 16));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
-    MOR_TRY(xfer.alloc(sizeof(double) * (size_t)(k + 2) * (size_t)(cx.nranks + 1)));
+    MOR_TRY(xfer.alloc(sizeof(double) * (size_t)rec * (size_t)(cx.nranks + 1)));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
     double* Wm = state.as<double>();
     double* Uf = Wm + kk;
@@ -374,24 +448,47 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* Z = Lm + kk;
     double* Zt = Z + kk;
     double* c = Zt + kk;
-    long long* idx_d = reinterpret_cast<long long*>(c + k);
+    double* bst = c + k;                  // block state
+    double* Cp = bst + bdoubles;          // packed panel coefficients
+    long long* idx_d = reinterpret_cast<long long*>(Cp + cp_doubles);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
     double* send = xfer.as<double>();
-    double* gathered = cx.nranks > 1 ? send + (k + 2) : send;
+    double* gathered = cx.nranks > 1 ? send + rec : send;
+    const size_t bb = (size_t)DEIM_BLOCK * DEIM_BLOCK;
 
-    Timer t_total(MOR_T_TOTAL), t_step(MOR_T_DEIM_STEP), t_tail(MOR_T_DEIM_TAIL);
+    Timer t_total(MOR_T_TOTAL), t_step(MOR_T_DEIM_STEP), t_tail(MOR_T_DEIM_TAIL), t_panel(MOR_T_DEIM_PANEL);
     t_total.start();
     for (int i = 0; i < (int)k; ++i) {
+        const int l0 = blocked ? (i / DEIM_BLOCK) * DEIM_BLOCK : 0;   // first column of the current block
+        const int j = i - l0;                                          // step inside the block
+        const int bw = blocked ? (int)(k - l0 < DEIM_BLOCK ? k - l0 : DEIM_BLOCK) : (int)k;
+        // the matrix the streaming kernel works on: the basis itself, or the residual panel of this block
+        const double* Pn = (blocked && l0 > 0) ? panel.as<double>() : B + (size_t)l0 * ld;
+        const int64_t ldn = (blocked && l0 > 0) ? ldp : ld;
+        const double* coef = blocked ? bst + 5 * bb : c;
+        if (blocked && j == 0 && l0 > 0) {
+            t_panel.start();
+            deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
+            count_launch();
+            if (m > 0) MOR_TRY(deim_panel(B, ld, l0, bw, Cp, m, panel.as<double>(), ldp));
+            t_panel.stop();
+        }
         t_step.start();
-        if (vec)
-            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+        const bool vec_n = vec || (blocked && l0 > 0);
+        if (vec_n)
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, j, coef, row_offset, cands.as<Cand>());
         else
-            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, j, coef, row_offset, cands.as<Cand>());
         t_step.stop();
         t_tail.start();
-        deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send);
-        if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)(k + 2)));
-        deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, i, (int)k, Wm, Uf, Lm, Z, Zt, c, idx_d, status_d);
+        deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send,
+                                                     blocked ? Pn : nullptr, ldn, bw);
+        if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)rec));
+        UpdArgs ua;
+        ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0};
+        ua.st[1] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
+                            2 + (int)k, 1};
+        deim_update_kernel<<<blocked ? 2 : 1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
         t_tail.stop();
         count_launch(3);
     }
@@ -405,6 +502,8 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     t_total.collect();
     t_step.collect();
     t_tail.collect();
+    t_panel.collect();
+    cx.timings[MOR_T_DEIM_BLOCKED] = blocked ? 1.0 : 0.0;
     for (int64_t i = 0; i < k; ++i) idx_host[i] = (int64_t)idx_h[(size_t)i];
     if (status_h != 0) {
         set_error("deim_interpolation_indices: P'U is exactly singular at step " + std::to_string(status_h + 1) +

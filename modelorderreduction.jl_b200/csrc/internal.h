@@ -132,6 +132,8 @@ int32_t kat_check_left(const double* U, int64_t m, int64_t ld, int k, int64_t n,
 
 // ---- DEIM (deim.cu) -------------------------------------------------------------------------
 int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host);
+// R (m x bw, ldr) = U[:, l0 : l0+bw] - U[:, 0 : l0] * C with C packed in 16-row slabs (deim_panel.cu)
+int32_t deim_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp, int64_t m, double* R, int64_t ldr);
 
 // ---- tall-skinny GEMMs on DMMA (gemm_tn.cu / gemm_nn.cu) -----------------------------------
 // C (p x q, ldc, column-major, both triangles when A == B) = A' * B, A: m x p, B: m x q.

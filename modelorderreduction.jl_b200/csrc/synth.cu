@@ -85,6 +85,92 @@ static int32_t launch_synth(double* X, int64_t m, int64_t n, int64_t ld, uint64_
 
 int32_t kat_fill(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double decades);
 
+// ---- 2-D viscous Burgers snapshots ---------------------------
+// Cole-Hopf closed form: with phi = sum_i exp(theta_i),
+//   theta_i = (-(p_i x + q_i y) + (p_i^2 + q_i^2) t / 2 + d_i) / (2 nu)      (phi_t = nu lap(phi)),
+// (u, v) = -2 nu grad(phi) / phi = softmax(theta)-weighted mean of the states (p_i, q_i) solves
+//   u_t + u u_x + v u_y = nu lap(u)  (same for v):
+// three constant states separated by travelling fronts of width ~ 4 nu / |p_i - p_j| that merge in a
+// moving triple point.  Row r of the snapshot matrix is grid node (ix, iy) = (r mod nx, r div nx) of the
+// u component, x = (ix + 1/2) / nx, y = (iy + 1/2) / nx; column j is time t_j = j / (n - 1).
+// The same closed form is restated in oracle/mor_oracle.py:burgers_snapshots.
+struct BurgersCoef {
+    double ax[3], ay[3], p[3];
+};
+
+static void burgers_states(uint64_t seed, double p[3], double q[3], double d[3]) {
+    // generic (not grid-commensurate) front directions: no two grid nodes see bit-identical histories
+    const double P[3] = {0.9371, 0.0283, -0.7619}, Q[3] = {0.2517, -0.5139, 0.4877}, D[3] = {0.0, -0.45, -0.55};
+    for (int i = 0; i < 3; ++i) {
+        p[i] = P[i];
+        q[i] = Q[i];
+        // the seed shifts the initial front positions by at most +-0.01 (multiples of 1/3200)
+        const uint64_t h = (seed * (uint64_t)(2 * i + 3)) & 63u;
+        d[i] = D[i] + ((double)h - 32.0) / 3200.0;
+    }
+}
+
+// one thread = one row, blockIdx.y = a group of 16 columns; tcoef[3 * j + i] = time part of theta_i in column j
+__global__ void __launch_bounds__(256)
+burgers_kernel(double* __restrict__ X, int64_t m, int64_t n, int64_t ld, int64_t row0, int64_t nx, BurgersCoef cf,
+               const double* __restrict__ tcoef) {
+    const int64_t j0 = (int64_t)blockIdx.y * 16, j1 = j0 + 16 < n ? j0 + 16 : n;
+    const double h = 1.0 / (double)nx;
+    for (int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; lr < m; lr += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = row0 + lr, iy = g / nx, ix = g - iy * nx;
+        const double x = ((double)ix + 0.5) * h, y = ((double)iy + 0.5) * h;
+        double s[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s[i] = cf.ax[i] * x + cf.ay[i] * y;
+        for (int64_t j = j0; j < j1; ++j) {
+            double th[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) th[i] = s[i] + __ldg(&tcoef[3 * j + i]);
+            const double mx = fmax(th[0], fmax(th[1], th[2]));
+            double num = 0.0, den = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double e = exp(th[i] - mx);
+                num += cf.p[i] * e;
+                den += e;
+            }
+            X[j * ld + lr] = num / den;
+        }
+    }
+}
+
+static int32_t burgers_fill(double* X, int64_t m, int64_t n, int64_t ld, uint64_t seed, int64_t row0, double nu,
+                            int64_t nx) {
+    MOR_ARG(nu > 0.0 && nx >= 1, "mor_b200_synth(BURGERS): param = viscosity > 0, iparam = grid width >= 1");
+    if (m == 0 || n == 0) return MOR_OK;
+    Ctx& c = ctx();
+    double p[3], q[3], d[3];
+    burgers_states(seed, p, q, d);
+    BurgersCoef cf;
+    std::vector<double> tc((size_t)(3 * n));
+    for (int i = 0; i < 3; ++i) {
+        cf.ax[i] = -p[i] / (2.0 * nu);
+        cf.ay[i] = -q[i] / (2.0 * nu);
+        cf.p[i] = p[i];
+    }
+    for (int64_t j = 0; j < n; ++j) {
+        const double t = n > 1 ? (double)j / (double)(n - 1) : 0.0;
+        for (int i = 0; i < 3; ++i) tc[(size_t)(3 * j + i)] = (0.5 * (p[i] * p[i] + q[i] * q[i]) * t + d[i]) / (2.0 * nu);
+    }
+    DevBuf dt;
+    MOR_TRY(dt.alloc(sizeof(double) * tc.size()));
+    MOR_CUDA(cudaMemcpyAsync(dt.p, tc.data(), sizeof(double) * tc.size(), cudaMemcpyHostToDevice, c.stream));
+    int64_t bx = (m + 255) / 256;
+    const int64_t cap = (int64_t)c.num_sms * 8;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)((n + 15) / 16));
+    burgers_kernel<<<grid, 256, 0, c.stream>>>(X, m, n, ld, row0, nx, cf, dt.as<double>());
+    count_launch();
+    MOR_CUDA(cudaGetLastError());
+    MOR_CUDA(cudaStreamSynchronize(c.stream));  // dt and tc are released on return
+    return MOR_OK;
+}
+
 int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, uint64_t seed,
                    int64_t row0, double param, int64_t iparam) {
     std::vector<double> scale((size_t)(n > 0 ? n : 1), 1.0);
@@ -107,6 +193,8 @@ int32_t synth_fill(double* X, int64_t m, int64_t n, int64_t ld, int32_t kind, ui
             break;
         case MOR_SYNTH_KAT:
             return kat_fill(X, m, n, ld, seed, row0, param);
+        case MOR_SYNTH_BURGERS:
+            return burgers_fill(X, m, n, ld, seed, row0, param, iparam);
         default:
             set_error("mor_b200_synth: unknown generator kind");
             return MOR_ERR_ARG;

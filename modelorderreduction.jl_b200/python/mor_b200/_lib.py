@@ -13,10 +13,10 @@ DEFAULT_LIB = _PKG_ROOT / "lib" / "libmor_b200.so"
 # status codes (include/mor_b200.h)
 OK, ERR_ARG, ERR_NONFINITE, ERR_CUDA, ERR_NOMEM, ERR_NOCONV, ERR_SINGULAR = range(7)
 MOR_SVD, MOR_TSVD, MOR_RSVD = 0, 1, 2
-SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK, SYNTH_KAT = 0, 1, 2, 3
+SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK, SYNTH_KAT, SYNTH_BURGERS = 0, 1, 2, 3, 4
 POD_MAY_OVERWRITE, POD_FORCE_TWO_PASS = 1, 2
 T_SLOTS = ("total", "h2d", "gram", "apply", "core", "basis", "comm", "deim_step", "deim_tail",
-           "d2h", "sketch")
+           "d2h", "sketch", "deim_panel", "deim_blocked")
 T_NSLOTS = 16
 
 

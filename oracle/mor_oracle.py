@@ -346,3 +346,40 @@ def subspace_sine(U_ref: Array, U: Array) -> float:
     Q, _ = np.linalg.qr(U)
     resid = Q - Qr @ (Qr.T @ Q)
     return float(np.linalg.norm(resid, 2))
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE config 5 input: 2-D viscous Burgers snapshots.
+# Not reference code -- the reference ships no Burgers model; this restates the closed form
+# the library's MOR_SYNTH_BURGERS generator (csrc/synth.cu) evaluates, so the generated
+# snapshot matrix can be checked entry by entry and against the PDE itself.
+# --------------------------------------------------------------------------------------
+def burgers_states(seed: int = 0):
+    """States (p_i, q_i) and phase offsets d_i of the three-front Cole-Hopf solution."""
+    P, Q, D = (0.9371, 0.0283, -0.7619), (0.2517, -0.5139, 0.4877), (0.0, -0.45, -0.55)
+    d = [D[i] + (float(((seed * (2 * i + 3)) & (2**64 - 1)) & 63) - 32.0) / 3200.0 for i in range(3)]
+    return np.array(P), np.array(Q), np.array(d)
+
+
+def burgers_field(x: Array, y: Array, t: float, nu: float, seed: int = 0) -> Tuple[Array, Array]:
+    """(u, v)(x, y, t) = -2 nu grad(phi)/phi with phi = sum_i exp(theta_i),
+    theta_i = (-(p_i x + q_i y) + (p_i^2 + q_i^2) t / 2 + d_i) / (2 nu): an exact solution of
+    u_t + u u_x + v u_y = nu lap(u), v_t + u v_x + v v_y = nu lap(v)."""
+    p, q, d = burgers_states(seed)
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    th = np.stack([(-p[i] / (2.0 * nu)) * x + (-q[i] / (2.0 * nu)) * y
+                   + (0.5 * (p[i] * p[i] + q[i] * q[i]) * t + d[i]) / (2.0 * nu) for i in range(3)])
+    e = np.exp(th - th.max(axis=0))
+    den = e.sum(axis=0)
+    return np.tensordot(p, e, axes=1) / den, np.tensordot(q, e, axes=1) / den
+
+
+def burgers_snapshots(m: int, n: int, nx: int, nu: float, seed: int = 0, row0: int = 0) -> Array:
+    """Rows [row0, row0 + m) of the m_global x n snapshot matrix of the u component: row r is grid
+    node (r mod nx, r div nx), x = (ix + 1/2)/nx, y = (iy + 1/2)/nx; column j is time j/(n-1)."""
+    g = row0 + np.arange(m, dtype=np.int64)
+    x, y = ((g % nx) + 0.5) * (1.0 / nx), ((g // nx) + 0.5) * (1.0 / nx)
+    X = np.empty((m, n), dtype=np.float64, order="F")
+    for j in range(n):
+        X[:, j] = burgers_field(x, y, j / (n - 1) if n > 1 else 0.0, nu, seed)[0]
+    return X

@@ -162,3 +162,69 @@ def test_calls_from_several_host_threads_serialise(gpu):
     assert got == want
     for s in pods:                      # orthonormal columns: all singular values are 1
         assert np.max(np.abs(s - 1.0)) < 1e-12
+
+
+def test_burgers_snapshots_generator_vs_closed_form(gpu):
+    """MOR_SYNTH_BURGERS (BASELINE config 5 input) against the oracle's restatement of the same Cole-Hopf
+    closed form: entry by entry, on ragged shards (row0 not a multiple of the grid width)."""
+    nx, n, nu = 96, 37, 1.5e-3
+    m = nx * 80 + 13
+    ref = O.burgers_snapshots(m, n, nx, nu, seed=9)
+    X = DeviceMatrix.alloc(m, n).synth(_lib.SYNTH_BURGERS, seed=9, param=nu, iparam=nx).to_host()
+    assert np.abs(X - ref).max() <= 1e-11
+    for row0, rows in ((0, 1), (101, 3001), (m - 7, 7)):
+        part = DeviceMatrix.alloc(rows, n).synth(_lib.SYNTH_BURGERS, seed=9, global_row0=row0, param=nu, iparam=nx)
+        assert np.array_equal(part.to_host(), X[row0:row0 + rows])     # shard invariant, bit for bit
+    with pytest.raises(ValueError):
+        DeviceMatrix.alloc(8, 2).synth(_lib.SYNTH_BURGERS, seed=0, param=0.0, iparam=4)
+
+
+def test_burgers_pod_basis_deim_config5(gpu):
+    """Config 5 end to end at oracle size: Burgers snapshots -> POD basis (library) -> DEIM indices,
+    indices bit-exact against the oracle on the same basis; sigma / subspace against dgesdd."""
+    from mor_b200.device import pod_factor_dev
+    nx, n, k = 256, 64, 64
+    m = nx * nx
+    S = DeviceMatrix.alloc(m, n).synth(_lib.SYNTH_BURGERS, seed=1, param=1e-3, iparam=nx)
+    Sh = S.to_host()
+    f = pod_factor_dev(S, _lib.MOR_SVD, k)
+    u_ref, s_ref, _ = O._svd(Sh)
+    assert O.sigma_error(s_ref, f.s) <= 1e-10
+    U = f.basis(k, DeviceMatrix.alloc(m, k))
+    Uh = U.to_host()
+    assert O.subspace_sine(u_ref[:, :16], Uh[:, :16]) <= 1e-8
+    assert np.abs(Uh.T @ Uh - np.eye(k)).max() <= 1e-10
+    idx = deim_indices_dev(U)
+    assert idx.tolist() == O.deim_interpolation_indices(Uh).tolist()
+    assert len(set(idx.tolist())) == k
+    # DEIM points of a front-dominated field sit on the swept region, not on the plateaus
+    swept = np.ptp(Sh, axis=1) > 0.1
+    assert swept[idx - 1].mean() > 0.9
+
+
+@pytest.mark.parametrize("m,k,seed", [(4097, 33, 1), (50_000, 17, 2), (70_001, 40, 3), (131_072, 64, 4), (20_000, 130, 5)])
+def test_blocked_and_streaming_paths_agree(gpu, monkeypatch, m, k, seed):
+    """k > 16 takes the blocked path (16-column residual panels, one pass over the earlier columns per block);
+    MOR_B200_DEIM_BLOCK=0 forces the streaming path.  Both must give the oracle's indices."""
+    rng = np.random.Generator(np.random.PCG64(500 + seed))
+    Q, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    Q = np.asfortranarray(Q)
+    want = O.deim_interpolation_indices(Q).tolist()
+    monkeypatch.delenv("MOR_B200_DEIM_BLOCK", raising=False)
+    assert mor_b200.deim_interpolation_indices(Q).tolist() == want
+    assert _lib.last_timings()["deim_blocked"] == 1.0 and _lib.last_timings()["deim_panel"] > 0
+    monkeypatch.setenv("MOR_B200_DEIM_BLOCK", "0")
+    assert mor_b200.deim_interpolation_indices(Q).tolist() == want
+    assert _lib.last_timings()["deim_blocked"] == 0.0
+
+
+def test_blocked_path_exact_ties_across_blocks(gpu, monkeypatch):
+    """Duplicated rows tie exactly in every residual; the lowest global index must win in every block."""
+    monkeypatch.delenv("MOR_B200_DEIM_BLOCK", raising=False)
+    rng = np.random.Generator(np.random.PCG64(77))
+    m, k = 30_000, 40
+    A = rng.standard_normal((m, k))
+    A[20_000:30_000] = A[5_000:15_000]            # every row of the second range duplicates one of the first
+    idx = mor_b200.deim_interpolation_indices(np.asfortranarray(A))
+    assert idx.tolist() == O.deim_interpolation_indices(A).tolist()
+    assert not np.any((idx > 20_000))             # the duplicate with the higher index never wins

@@ -121,3 +121,16 @@ def test_jacobi_svd(gpu, rows, n, kappa):
     assert np.max(np.abs(Vh.T @ Vh - np.eye(n))) < 2e-12
     assert rel(A @ Vh, Ah) < 1e-13
     assert 1 <= sweeps.value <= 40   # no de Rijk / Drmac-Veselic preconditioning yet: generic kappa=1e8 input takes ~30 sweeps
+
+
+@pytest.mark.parametrize("m,l0,bw", [(1, 16, 16), (127, 16, 3), (128, 32, 16), (129, 48, 16), (4099, 240, 16),
+                                     (50_001, 112, 9), (300_000, 64, 16)])
+def test_deim_panel_residual(gpu, m, l0, bw):
+    """deim_panel_kernel: R = U[:, l0:l0+bw] - U[:, :l0] C (the residual panel of the blocked DEIM path)."""
+    rng = np.random.default_rng(m + l0 + bw)
+    U = rng.standard_normal((m, l0 + bw)); Cm = rng.standard_normal((l0, bw))
+    dU, dC, dR = DeviceMatrix.from_host(U), DeviceMatrix.from_host(Cm), DeviceMatrix.alloc(m, 16)
+    _dbg(gpu, "mor_dbg_deim_panel", dU.handle, l0, bw, dC.handle, dR.handle)
+    got = dR.to_host()[:, :bw]
+    ref = U[:, l0:] - U[:, :l0] @ Cm
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.sqrt(l0)

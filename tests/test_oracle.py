@@ -152,3 +152,34 @@ def test_parity_metrics():
     assert O.sigma_error(s, s + np.array([0, 0, 1e-12])) == pytest.approx(1e-12)
     Q, _ = np.linalg.qr(np.random.default_rng(0).standard_normal((50, 4)))
     assert O.subspace_sine(Q, -Q[:, ::-1]) < 1e-14
+
+
+def test_burgers_closed_form_solves_the_pde():
+    """BASELINE config 5 input: the Cole-Hopf field the MOR_SYNTH_BURGERS generator
+    evaluates must satisfy u_t + u u_x + v u_y = nu lap(u) (central differences, nu large enough for FD)."""
+    nu, h, t = 0.02, 1e-4, 0.37
+    x, y = np.meshgrid(np.linspace(0.05, 0.95, 41), np.linspace(0.05, 0.95, 37))
+    f = lambda dx=0.0, dy=0.0, dt=0.0: O.burgers_field(x + dx, y + dy, t + dt, nu, seed=5)
+    for comp in (0, 1):
+        w = f()[comp]
+        u, v = f()
+        wx = (f(h)[comp] - f(-h)[comp]) / (2 * h)
+        wy = (f(0, h)[comp] - f(0, -h)[comp]) / (2 * h)
+        wt = (f(0, 0, h)[comp] - f(0, 0, -h)[comp]) / (2 * h)
+        lap = (f(h)[comp] + f(-h)[comp] + f(0, h)[comp] + f(0, -h)[comp] - 4 * w) / h**2
+        assert np.abs(wt + u * wx + v * wy - nu * lap).max() < 1e-4 * np.abs(u * wx).max()
+
+
+def test_burgers_snapshots_layout_and_shard_invariance():
+    nx, n, nu = 48, 12, 2e-3
+    X = O.burgers_snapshots(nx * 40, n, nx, nu, seed=3)
+    assert X.shape == (nx * 40, n) and X.flags.f_contiguous
+    # (numpy's SIMD exp may differ in the last bit between the body and the tail of an array)
+    assert np.allclose(X[777:1500], O.burgers_snapshots(723, n, nx, nu, seed=3, row0=777), rtol=0, atol=1e-14)
+    p, _, d = O.burgers_states(3)
+    assert p.min() - 1e-12 <= X.min() and X.max() <= p.max() + 1e-12      # a convex combination of the states
+    assert len({round(v, 6) for v in X[:, 0]} & {round(v, 6) for v in p}) == 3   # all three plateaus are in the domain
+    assert np.all(np.abs(d - np.array([0.0, -0.45, -0.55])) <= 0.01 + 1e-15)
+    # the fronts travel: snapshots are linearly independent (slow singular value decay)
+    s = sla.svd(X, compute_uv=False)
+    assert s[-1] / s[0] > 1e-6
