@@ -5,41 +5,54 @@
 // columns (the reference, and the streaming deim_step_kernel, re-read them once per column).
 //
 // Design (B200): HBM-bound -- 8 m (l0 + bw) bytes read, 8 m bw written, 2 m l0 bw flop (4 flop/B at
-// bw = 16, below the FP64 tensor balance of ~5.3).  Persistent CTAs (one per SM) walk 128-row tiles;
-// a producer warp streams, through a 6-stage mbarrier ring that runs ahead across tile boundaries,
-// sixteen 1 KB 1-D bulk copies per stage (16 basis columns x 128 rows, shared row stride 132 doubles)
-// plus the matching 16 x 16 slab of C (stride 20), both = 4 (mod 16) eight-byte banks: conflict-free
-// DMMA.8x8x4 fragment loads.  The last stage of every tile carries the bw columns U[:, l0 : l0+bw]
-// themselves, so the epilogue (subtract, store) also reads from shared memory.  Eight consumer warps
-// own 16 rows x 16 columns each (2 x 2 DMMA tiles).
+// bw = 16, below the FP64 tensor balance of ~5.3).  Persistent CTAs (one per SM) walk row tiles; a
+// producer warp streams, through a 6-stage mbarrier ring that runs ahead across tile boundaries, KC
+// 1-D bulk copies per stage (KC basis columns x RT rows, RT * KC = 2048 doubles; default 256 rows x 8
+// columns = 2 KB contiguous runs; shared row stride RT + 4 doubles) plus the matching 16 x 16 slab of C
+// (stride 20), both = 4 (mod 16) eight-byte banks: conflict-free DMMA.8x8x4 fragment loads.  The last
+// stages of every tile carry the bw columns U[:, l0 : l0+bw] themselves, so the epilogue (subtract, store)
+// also reads from shared memory.  Eight consumer warps own RT / 8 rows x 16 columns each.
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
 namespace mor {
 namespace {
 
-constexpr int PN_RT = 128;      // rows per tile
-constexpr int PN_BW = 16;       // panel width = columns per stage
-constexpr int PN_RS = 132;      // shared row-tile stride (doubles)
+constexpr int PN_BW = 16;       // panel width = columns per C slab
 constexpr int PN_CS = 20;       // shared C slab stride (doubles)
-constexpr int PN_STAGES = 6;
-constexpr int PN_XS = PN_BW * PN_RS;          // 2112 doubles
 constexpr int PN_SLAB = PN_BW * PN_CS;        // 320 doubles
-constexpr int PN_STAGE = PN_XS + PN_SLAB;     // 2432 doubles = 19456 B
+constexpr int PN_STAGES = 6;
 constexpr int PN_WARPS = 8;
 constexpr int PN_THREADS = PN_WARPS * 32 + 32;
-constexpr size_t PN_SMEM = (size_t)PN_STAGES * PN_STAGE * 8 + 2 * PN_STAGES * 8 + 128;
 
+// RT rows per tile x KC basis columns per stage (RT * KC = 2048 doubles = 16 KB of basis per stage):
+// a stage is KC bulk copies of RT * 8 contiguous bytes each -- the longer the run, the fewer DRAM pages
+// a stage touches.
+template <int RT, int KC>
+struct PanelCfg {
+    static constexpr int RS = RT + 4;               // shared row-tile stride (doubles), = 4 (mod 16) banks
+    static constexpr int XS = KC * RS;
+    static constexpr int STAGE = XS + PN_SLAB;      // doubles
+    static constexpr int MI = RT / (8 * PN_WARPS);  // 8-row DMMA tiles per warp
+    static constexpr size_t SMEM = (size_t)PN_STAGES * STAGE * 8 + 2 * PN_STAGES * 8 + 128;
+};
+
+template <int RT, int KC>
 __global__ void __launch_bounds__(PN_THREADS, 1)
 deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, const double* __restrict__ Cp,
                   long long m, double* __restrict__ R, long long ldr) {
+    using Cfg = PanelCfg<RT, KC>;
+    constexpr int RS = Cfg::RS, XS = Cfg::XS, STAGE = Cfg::STAGE, MI = Cfg::MI;
     extern __shared__ unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)PN_STAGES * PN_STAGE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)PN_STAGES * STAGE);
     uint64_t* empty = full + PN_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tiles = (m + PN_RT - 1) / PN_RT;
-    const int nch = l0 / PN_BW;   // l0 is a multiple of 16
+    const long long tiles = (m + RT - 1) / RT;
+    const int nst = l0 / KC;                    // MMA stages per tile (l0 is a multiple of 16)
+    const int nep = (bw + KC - 1) / KC;         // epilogue stages per tile (the panel's own columns)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PN_STAGES; ++s) {
@@ -51,28 +64,28 @@ deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, co
     __syncthreads();
 
     if (warp == PN_WARPS) {
-        // ---- producer warp: lanes 0..15 copy one column segment each, lane 0 also the C slab ----
+        // ---- producer warp: lanes 0..KC-1 copy one column segment each, lane 0 also the C slab ----
         int stage = 0;
         uint32_t phase = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const long long r0 = tile * PN_RT;
+            const long long r0 = tile * RT;
             long long rows = m - r0;
-            if (rows > PN_RT) rows = PN_RT;
+            if (rows > RT) rows = RT;
             const uint32_t row_bytes = (uint32_t)(((rows + 1) & ~1LL) * 8);   // 16-byte multiple
-            for (int c = 0; c <= nch; ++c) {
-                const bool last = c == nch;
-                const int ncol = last ? bw : PN_BW;
+            for (int c = 0; c < nst + nep; ++c) {
+                const bool ep = c >= nst;
+                int ncol = KC;
+                if (ep && (c - nst + 1) * KC > bw) ncol = bw - (c - nst) * KC;
                 if (lane == 0) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full[stage], (uint32_t)(ncol * row_bytes + (last ? 0 : PN_SLAB * 8)));
+                    ptx::mbar_expect_tx(&full[stage], (uint32_t)(ncol * row_bytes + (ep ? 0 : PN_SLAB * 8)));
                 }
                 __syncwarp();
-                double* dst = ring + (size_t)stage * PN_STAGE;
+                double* dst = ring + (size_t)stage * STAGE;
                 if (lane < ncol)
-                    ptx::bulk_load_1d(dst + lane * PN_RS, U + (size_t)(c * PN_BW + lane) * ld + r0, row_bytes,
-                                      &full[stage]);
-                if (lane == 0 && !last)
-                    ptx::bulk_load_1d(dst + PN_XS, Cp + (size_t)c * PN_SLAB, PN_SLAB * 8, &full[stage]);
+                    ptx::bulk_load_1d(dst + lane * RS, U + (size_t)(c * KC + lane) * ld + r0, row_bytes, &full[stage]);
+                if (lane == 0 && !ep)
+                    ptx::bulk_load_1d(dst + XS, Cp + (size_t)((c * KC) / PN_BW) * PN_SLAB, PN_SLAB * 8, &full[stage]);
                 if (++stage == PN_STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -82,34 +95,34 @@ deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, co
         return;
     }
 
-    // ---- consumer warps: warp w owns rows 16 w .. 16 w + 15 of the tile, all 16 columns ----------
-    const int wm0 = warp * 16;
+    // ---- consumer warps: warp w owns rows 8 MI w .. 8 MI (w + 1) - 1 of the tile, all 16 columns -------
+    const int wm0 = warp * 8 * MI;
     const int g = lane >> 2, tq = lane & 3;
     int stage = 0;
     uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long r0 = tile * PN_RT;
+        const long long r0 = tile * RT;
         long long rows = m - r0;
-        if (rows > PN_RT) rows = PN_RT;
-        double acc[2][2][2];
+        if (rows > RT) rows = RT;
+        double acc[MI][2][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int c = 0; c < nch; ++c) {
+        for (int c = 0; c < nst; ++c) {
             ptx::mbar_wait(&full[stage], phase);
-            const double* Xs = ring + (size_t)stage * PN_STAGE;
-            const double* ap = Xs + tq * PN_RS + wm0 + g;
-            const double* bp = Xs + PN_XS + g * PN_CS + tq;
+            const double* Xs = ring + (size_t)stage * STAGE;
+            const double* ap = Xs + tq * RS + wm0 + g;
+            const double* bp = Xs + XS + g * PN_CS + ((c * KC) % PN_BW) + tq;
 #pragma unroll
-            for (int s = 0; s < PN_BW / 4; ++s) {
-                double a[2], b[2];
+            for (int s = 0; s < KC / 4; ++s) {
+                double a[MI], b[2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) a[i] = ap[4 * s * PN_RS + 8 * i];
+                for (int i = 0; i < MI; ++i) a[i] = ap[4 * s * RS + 8 * i];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) b[j] = bp[8 * j * PN_CS + 4 * s];
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) ptx::dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
@@ -120,30 +133,51 @@ deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, co
                 phase ^= 1;
             }
         }
-        // epilogue stage: the panel's own columns; R = U_blk - acc
-        ptx::mbar_wait(&full[stage], phase);
-        {
-            const double* Xs = ring + (size_t)stage * PN_STAGE;
+        // epilogue stages: the panel's own columns, KC at a time; R = U_blk - acc
+        for (int e = 0; e < nep; ++e) {
+            ptx::mbar_wait(&full[stage], phase);
+            const double* Xs = ring + (size_t)stage * STAGE;
+            const int c0 = e * KC;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < MI; ++i) {
                 const long long r = wm0 + 8 * i + g;
                 if (r < rows) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int col = 8 * j + 2 * tq;
-                        if (col < bw) R[(size_t)col * ldr + r0 + r] = Xs[col * PN_RS + r] - acc[i][j][0];
-                        if (col + 1 < bw) R[(size_t)(col + 1) * ldr + r0 + r] = Xs[(col + 1) * PN_RS + r] - acc[i][j][1];
-                    }
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int col = 8 * j + 2 * tq + h;
+                            if (col >= c0 && col < c0 + KC && col < bw)
+                                R[(size_t)col * ldr + r0 + r] = Xs[(col - c0) * RS + r] - acc[i][j][h];
+                        }
                 }
             }
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[stage]);
-        if (++stage == PN_STAGES) {
-            stage = 0;
-            phase ^= 1;
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+            if (++stage == PN_STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
         }
     }
+}
+
+template <int RT, int KC>
+int32_t launch_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp, int64_t m, double* R, int64_t ldr) {
+    using Cfg = PanelCfg<RT, KC>;
+    Ctx& cx = ctx();
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel<RT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int64_t tiles = (m + RT - 1) / RT;
+    const int grid = (int)(tiles < (int64_t)cx.num_sms ? tiles : (int64_t)cx.num_sms);
+    deim_panel_kernel<RT, KC><<<grid, PN_THREADS, Cfg::SMEM, cx.stream>>>(U, ld, l0, bw, Cp, m, R, ldr);
+    MOR_CUDA(cudaGetLastError());
+    count_launch();
+    return MOR_OK;
 }
 
 }  // namespace
@@ -156,18 +190,14 @@ int32_t deim_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp
     MOR_ARG(ld % 2 == 0 && (uintptr_t)U % 16 == 0 && ld >= ((m + 1) & ~int64_t(1)),
             "deim_panel: the basis must be 16-byte aligned with an even leading dimension >= m rounded up to even");
     if (m == 0) return MOR_OK;
-    Ctx& cx = ctx();
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PN_SMEM));
-        attr_set = true;
-    }
-    const int64_t tiles = (m + PN_RT - 1) / PN_RT;
-    const int grid = (int)(tiles < (int64_t)cx.num_sms ? tiles : (int64_t)cx.num_sms);
-    deim_panel_kernel<<<grid, PN_THREADS, PN_SMEM, cx.stream>>>(U, ld, l0, bw, Cp, m, R, ldr);
-    MOR_CUDA(cudaGetLastError());
-    count_launch();
-    return MOR_OK;
+    // Tile shape, measured at 16M x 256 on B200 (sum of the 15 panel launches, 322 GB of traffic):
+    // 128 x 16 (1 KB runs) 82.4 ms, 256 x 8 (2 KB runs) 54.6 ms = 5.9 TB/s, 512 x 4 (4 KB runs, one k-step
+    // per stage) 73.2 ms.  MOR_B200_PANEL_TILE selects the other shapes (tests, experiments).
+    const char* v = getenv("MOR_B200_PANEL_TILE");
+    const int rt = v ? atoi(v) : 256;
+    if (rt == 512) return launch_panel<512, 4>(U, ld, l0, bw, Cp, m, R, ldr);
+    if (rt == 128) return launch_panel<128, 16>(U, ld, l0, bw, Cp, m, R, ldr);
+    return launch_panel<256, 8>(U, ld, l0, bw, Cp, m, R, ldr);
 }
 
 }  // namespace mor
