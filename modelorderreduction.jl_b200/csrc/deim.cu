@@ -440,7 +440,10 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
     MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k + bdoubles + cp_doubles) + sizeof(long long) * k + 16));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
-    MOR_TRY(xfer.alloc(sizeof(double) * (size_t)rec * (size_t)(cx.nranks + 1)));
+    // one record slot per greedy step: the update of the k x k factors (blocked path: on the side stream) may
+    // still be reading step i's record while step i+1's is being written
+    const size_t slot = (size_t)rec * (size_t)(cx.nranks + 1);
+    MOR_TRY(xfer.alloc(sizeof(double) * slot * (size_t)(blocked ? k : 1)));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
     double* Wm = state.as<double>();
     double* Uf = Wm + kk;
@@ -452,9 +455,19 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* Cp = bst + bdoubles;          // packed panel coefficients
     long long* idx_d = reinterpret_cast<long long*>(Cp + cp_doubles);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
-    double* send = xfer.as<double>();
-    double* gathered = cx.nranks > 1 ? send + rec : send;
     const size_t bb = (size_t)DEIM_BLOCK * DEIM_BLOCK;
+    // Blocked path: inside a block only the 16 x 16 factors of the panel decide the next coefficients, so the
+    // (much longer) bordered update of the k x k factors runs on a side stream, off the per-step latency chain;
+    // the main stream joins it at the next block boundary, where the panel coefficients need Z and Uf.
+    cudaEvent_t ev_rec = nullptr, ev_side = nullptr;
+    if (blocked) {
+        if (!cx.copy_stream) MOR_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
+        MOR_CUDA(cudaEventCreateWithFlags(&ev_rec, cudaEventDisableTiming));
+        MOR_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));          // the memset above
+        MOR_CUDA(cudaStreamWaitEvent(cx.copy_stream, ev_rec, 0));
+    }
+    cudaStream_t side = blocked ? cx.copy_stream : cx.stream;
 
     Timer t_total(MOR_T_TOTAL), t_step(MOR_T_DEIM_STEP), t_tail(MOR_T_DEIM_TAIL), t_panel(MOR_T_DEIM_PANEL);
     t_total.start();
@@ -466,7 +479,11 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         const double* Pn = (blocked && l0 > 0) ? panel.as<double>() : B + (size_t)l0 * ld;
         const int64_t ldn = (blocked && l0 > 0) ? ldp : ld;
         const double* coef = blocked ? bst + 5 * bb : c;
+        double* send = xfer.as<double>() + (blocked ? slot * (size_t)i : 0);
+        double* gathered = cx.nranks > 1 ? send + rec : send;
         if (blocked && j == 0 && l0 > 0) {
+            MOR_CUDA(cudaEventRecord(ev_side, side));           // all earlier updates of the k x k factors
+            MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
             t_panel.start();
             deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
             count_launch();
@@ -488,9 +505,24 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0};
         ua.st[1] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
                             2 + (int)k, 1};
-        deim_update_kernel<<<blocked ? 2 : 1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
+        if (blocked) {
+            MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));       // record i is complete
+            MOR_CUDA(cudaStreamWaitEvent(side, ev_rec, 0));
+            deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
+            UpdArgs ub;
+            ub.st[0] = ua.st[1];
+            ub.st[1] = ua.st[1];
+            deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
+            count_launch(4);
+        } else {
+            deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
+            count_launch(3);
+        }
         t_tail.stop();
-        count_launch(3);
+    }
+    if (blocked) {
+        MOR_CUDA(cudaEventRecord(ev_side, side));
+        MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
     }
     t_total.stop();
     MOR_CUDA(cudaGetLastError());
@@ -503,6 +535,8 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     t_step.collect();
     t_tail.collect();
     t_panel.collect();
+    if (ev_rec) cudaEventDestroy(ev_rec);
+    if (ev_side) cudaEventDestroy(ev_side);
     cx.timings[MOR_T_DEIM_BLOCKED] = blocked ? 1.0 : 0.0;
     for (int64_t i = 0; i < k; ++i) idx_host[i] = (int64_t)idx_h[(size_t)i];
     if (status_h != 0) {
