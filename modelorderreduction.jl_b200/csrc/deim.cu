@@ -89,6 +89,7 @@ __device__ __forceinline__ void cand_take(double& bv, long long& bi, double v, l
 
 constexpr int DEIM_THREADS = 256;
 constexpr int DEIM_BLOCK = 16;   // panel width of the blocked path (= the 16-column stages of deim_panel_kernel)
+constexpr int DEIM_SUB = 4;      // sub-panel width inside a panel (deim_step4_kernel)
 
 // Fused residual + abs-argmax over this rank's rows.  l = number of previous columns.
 // VEC: 16-byte loads (needs 16B-aligned base and even ld).  Each CTA walks chunks of
@@ -190,13 +191,114 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
     }
 }
 
+// Second blocking level: residuals of the next sw <= 4 columns of a panel P1 with respect to the s0 <= 12
+// interpolation points already chosen inside that panel,
+//     R2[:, q] = P1[:, s0 + q] - sum_{t < s0} P1[:, t] * D[t][q],
+// written to the sub-panel R2 and fused with the abs-argmax of its first column (= the next greedy step).
+// One streaming pass over s0 + sw panel columns instead of one pass per greedy step.  D: 16 x 4 column-major.
+template <int R>
+__global__ void __launch_bounds__(DEIM_THREADS)
+deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0, int sw, const double* __restrict__ Dg,
+                  double* __restrict__ R2, int64_t ld2, int64_t row_offset, Cand* __restrict__ out) {
+    __shared__ double sd[DEIM_BLOCK * DEIM_SUB];
+    __shared__ double sv[DEIM_THREADS / 32];
+    __shared__ long long si[DEIM_THREADS / 32];
+    const int tid = threadIdx.x;
+    if (tid < DEIM_BLOCK * DEIM_SUB) sd[tid] = Dg[tid];
+    __syncthreads();
+
+    const int64_t CH = 2 * R * DEIM_THREADS;
+    const int64_t nchunks = (m + CH - 1) / CH;
+    double bv = -1.0;
+    long long bi = MOR_IDX_NONE;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t c0 = chunk * CH;
+        if (c0 + CH <= m) {
+            double2 acc[R][DEIM_SUB];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int q = 0; q < DEIM_SUB; ++q) acc[r][q] = make_double2(0.0, 0.0);
+            const double* p = P1 + c0 + 2 * tid;
+#pragma unroll 2
+            for (int t = 0; t < s0; ++t) {
+                double2 v[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[r] = ld_stream2(p + r * (2 * DEIM_THREADS));
+#pragma unroll
+                for (int q = 0; q < DEIM_SUB; ++q) {
+                    const double d = sd[q * DEIM_BLOCK + t];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r][q].x = fma(v[r].x, d, acc[r][q].x);
+                        acc[r][q].y = fma(v[r].y, d, acc[r][q].y);
+                    }
+                }
+                p += ld1;
+            }
+#pragma unroll
+            for (int q = 0; q < DEIM_SUB; ++q) {
+                if (q < sw) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int64_t row = c0 + 2 * tid + r * (2 * DEIM_THREADS);
+                        const double2 u = ld_stream2(p + r * (2 * DEIM_THREADS));
+                        const double2 res = make_double2(u.x - acc[r][q].x, u.y - acc[r][q].y);
+                        *reinterpret_cast<double2*>(R2 + (int64_t)q * ld2 + row) = res;
+                        if (q == 0) {
+                            cand_take(bv, bi, fabs(res.x), row_offset + row);
+                            cand_take(bv, bi, fabs(res.y), row_offset + row + 1);
+                        }
+                    }
+                }
+                p += ld1;
+            }
+        } else {  // ragged last chunk
+            for (int64_t row = c0 + tid; row < m; row += DEIM_THREADS) {
+                double acc[DEIM_SUB] = {0.0, 0.0, 0.0, 0.0};
+                const double* p = P1 + row;
+                for (int t = 0; t < s0; ++t) {
+                    const double v = p[(int64_t)t * ld1];
+#pragma unroll
+                    for (int q = 0; q < DEIM_SUB; ++q) acc[q] = fma(v, sd[q * DEIM_BLOCK + t], acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < DEIM_SUB; ++q) {
+                    if (q < sw) {
+                        const double res = p[(int64_t)(s0 + q) * ld1] - acc[q];
+                        R2[(int64_t)q * ld2 + row] = res;
+                        if (q == 0) cand_take(bv, bi, fabs(res), row_offset + row);
+                    }
+                }
+            }
+        }
+    }
+    cand_block_reduce<DEIM_THREADS / 32>(bv, bi, sv, si);
+    if (tid == 0) {
+        out[blockIdx.x].val = bv;
+        out[blockIdx.x].idx = bi;
+    }
+}
+
+// D (16 x 4 column-major, zero padded) = Zb[0:s0, 0:s0] * Ufb[0:s0, s0 : s0+sw] from the panel's own factors
+// (row-major with stride kb): column q solves (P'P1_s0) d = P'P1[:, s0+q].
+__global__ void __launch_bounds__(DEIM_BLOCK * DEIM_SUB)
+deim_sub_coef_kernel(const double* __restrict__ Zb, const double* __restrict__ Ufb, int kb, int s0, int sw,
+                     double* __restrict__ D) {
+    const int t = threadIdx.x % DEIM_BLOCK, q = threadIdx.x / DEIM_BLOCK;
+    double s = 0.0;
+    if (t < s0 && q < sw)
+        for (int r = t; r < s0; ++r) s = fma(Zb[t * kb + r], Ufb[r * kb + s0 + q], s);
+    D[q * DEIM_BLOCK + t] = s;
+}
+
 // Reduce the per-CTA candidates of this rank and gather the winner's basis row:
 // send = [value, bits(global index), U[idx, 0..k)]
 // (blocked path: followed by the winner's row of the current residual panel, Pn[idx, 0..bw), padded to 16)
 __global__ void __launch_bounds__(1024)
 deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __restrict__ U, int64_t ld,
                   int64_t row_offset, int k, double* __restrict__ send, const double* __restrict__ Pn,
-                  int64_t ldp, int bw) {
+                  int64_t ldp, int bw, const double* __restrict__ P2, int64_t ld2, int sw) {
     __shared__ double sv[32];
     __shared__ long long si[32];
     __shared__ long long widx;
@@ -223,6 +325,10 @@ deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __res
     if (Pn != nullptr && threadIdx.x < DEIM_BLOCK)
         send[2 + k + threadIdx.x] =
             (g == MOR_IDX_NONE || (int)threadIdx.x >= bw) ? 0.0 : Pn[(g - row_offset) + (int64_t)threadIdx.x * ldp];
+    if (P2 != nullptr && threadIdx.x >= 32 && threadIdx.x < 32 + DEIM_SUB) {
+        const int q = threadIdx.x - 32;
+        send[2 + k + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= sw) ? 0.0 : P2[(g - row_offset) + (int64_t)q * ld2];
+    }
 }
 
 __device__ __forceinline__ double warp_sum(double s) {
@@ -421,7 +527,7 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     const int64_t ldp = (m + 1) & ~int64_t(1);
     bool blocked = deim_blocked_enabled() && k > DEIM_BLOCK && (m == 0 || (vec && ld >= ldp));
     DevBuf panel;
-    if (blocked && m > 0 && panel.alloc(sizeof(double) * (size_t)ldp * DEIM_BLOCK) != MOR_OK) {
+    if (blocked && m > 0 && panel.alloc(sizeof(double) * (size_t)ldp * (DEIM_BLOCK + DEIM_SUB)) != MOR_OK) {
         cudaGetLastError();   // no room for the panel: the streaming path needs no workspace
         blocked = false;
     }
@@ -433,10 +539,13 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     }
 
     const size_t kk = (size_t)k * k;
-    const int rec = (int)k + 2 + (blocked ? DEIM_BLOCK : 0);   // gathered record: value, index, basis row, panel row
+    // gathered record: value, index, basis row, panel row (16), sub-panel row (4)
+    const int rec = (int)k + 2 + (blocked ? DEIM_BLOCK + DEIM_SUB : 0);
     DevBuf state, cands, xfer;
     // state: Wm, Uf, Lm, Z, Zt (k*k each), c (k), idx (k int64), status; block state: 5 * 16*16 + 16; packed C
-    const size_t bdoubles = 5 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK;
+    // block state 5 * 16*16 + 16, sub-block state 5 * 4*4 + 4, sub-panel coefficients D 16 x 4
+    const size_t bdoubles = 5 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK + 5 * DEIM_SUB * DEIM_SUB + DEIM_SUB +
+                            DEIM_BLOCK * DEIM_SUB;
     const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
     MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k + bdoubles + cp_doubles) + sizeof(long long) * k + 16));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
@@ -455,7 +564,10 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* Cp = bst + bdoubles;          // packed panel coefficients
     long long* idx_d = reinterpret_cast<long long*>(Cp + cp_doubles);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
-    const size_t bb = (size_t)DEIM_BLOCK * DEIM_BLOCK;
+    const size_t bb = (size_t)DEIM_BLOCK * DEIM_BLOCK, ss = (size_t)DEIM_SUB * DEIM_SUB;
+    double* sst = bst + 5 * bb + DEIM_BLOCK;        // sub-block state
+    double* Dsub = sst + 5 * ss + DEIM_SUB;         // sub-panel coefficients
+    double* R2 = blocked && m > 0 ? panel.as<double>() + (size_t)ldp * DEIM_BLOCK : nullptr;
     // Blocked path: inside a block only the 16 x 16 factors of the panel decide the next coefficients, so the
     // (much longer) bordered update of the k x k factors runs on a side stream, off the per-step latency chain;
     // the main stream joins it at the next block boundary, where the panel coefficients need Z and Uf.
@@ -478,7 +590,12 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         // the matrix the streaming kernel works on: the basis itself, or the residual panel of this block
         const double* Pn = (blocked && l0 > 0) ? panel.as<double>() : B + (size_t)l0 * ld;
         const int64_t ldn = (blocked && l0 > 0) ? ldp : ld;
-        const double* coef = blocked ? bst + 5 * bb : c;
+        // second level: sub-panels of 4 columns inside the panel
+        const int s0 = blocked ? (j / DEIM_SUB) * DEIM_SUB : 0;       // first panel column of the current sub-panel
+        const int jj = j - s0;                                        // step inside the sub-panel
+        const int sw = blocked ? (bw - s0 < DEIM_SUB ? bw - s0 : DEIM_SUB) : 0;
+        const double* P2 = (blocked && s0 > 0) ? R2 : Pn + (size_t)s0 * ldn;
+        const int64_t ld2 = (blocked && s0 > 0) ? ldp : ldn;
         double* send = xfer.as<double>() + (blocked ? slot * (size_t)i : 0);
         double* gathered = cx.nranks > 1 ? send + rec : send;
         if (blocked && j == 0 && l0 > 0) {
@@ -491,28 +608,38 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
             t_panel.stop();
         }
         t_step.start();
-        const bool vec_n = vec || (blocked && l0 > 0);
-        if (vec_n)
-            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, j, coef, row_offset, cands.as<Cand>());
-        else
-            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, j, coef, row_offset, cands.as<Cand>());
+        if (blocked && s0 > 0 && jj == 0) {
+            // residuals of the next 4 panel columns in one pass over the s0 earlier ones, fused with this step's argmax
+            deim_sub_coef_kernel<<<1, DEIM_BLOCK * DEIM_SUB, 0, cx.stream>>>(bst + 3 * bb, bst + bb, bw, s0, sw, Dsub);
+            deim_step4_kernel<R><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, s0, sw, Dsub, R2, ldp, row_offset,
+                                                                       cands.as<Cand>());
+            count_launch();
+        } else if (blocked) {
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(P2, m, ld2, jj, sst + 5 * ss, row_offset,
+                                                                            cands.as<Cand>());
+        } else if (vec) {
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+        } else {
+            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+        }
         t_step.stop();
         t_tail.start();
         deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send,
-                                                     blocked ? Pn : nullptr, ldn, bw);
+                                                     blocked ? Pn : nullptr, ldn, bw, blocked ? P2 : nullptr, ld2, sw);
         if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)rec));
         UpdArgs ua;
         ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0};
-        ua.st[1] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
-                            2 + (int)k, 1};
+        ua.st[1] = ua.st[0];
         if (blocked) {
             MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));       // record i is complete
             MOR_CUDA(cudaStreamWaitEvent(side, ev_rec, 0));
             deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
-            UpdArgs ub;
-            ub.st[0] = ua.st[1];
-            ub.st[1] = ua.st[1];
-            deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
+            UpdArgs ub;   // the panel's 16 x 16 factors and the sub-panel's 4 x 4 factors: two CTAs of one launch
+            ub.st[0] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
+                                2 + (int)k, 1};
+            ub.st[1] = UpdState{sst, sst + ss, sst + 2 * ss, sst + 3 * ss, sst + 4 * ss, sst + 5 * ss, nullptr, jj, sw,
+                                2 + (int)k + DEIM_BLOCK, 1};
+            deim_update_kernel<<<2, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
             count_launch(4);
         } else {
             deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
