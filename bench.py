@@ -485,6 +485,27 @@ def run_ours(args):
     del os.environ["MOR_B200_DEIM_BLOCK"]
     stream_ms = max_over_ranks(e0.elapsed_time(e1) / 2)
     stream_step_ms = max_over_ranks(sacc["deim_step"] / 2)
+    # If the two paths part ways, show that the step where they do is a tie within rounding: residuals of BOTH
+    # candidate rows at that step, from the common earlier points, recomputed independently by torch (fp64).
+    # (On a smooth field sampled at 16M nodes the best rows are neighbours along a front; their residuals agree
+    # to ~1e-12 relative, the size of the rounding differences between two summation orders.)
+    first_diff = None
+    if np.any(idx_s != idx) and world == 1:
+        try:
+            t_ = int(np.flatnonzero(idx_s != idx)[0])
+            bm, bn, bld, bptr = B.info
+            bt = torch.as_tensor(_Alias(bptr, bn, bld), device="cuda")          # (k, ld): row j = basis column j
+            Pp = torch.from_numpy(idx[:t_] - 1).cuda()
+            cand = torch.tensor([int(idx[t_]) - 1, int(idx_s[t_]) - 1], device="cuda")
+            Wp = bt[:t_, :][:, Pp].T                                           # P'U_t   (t x t)
+            cc = torch.linalg.solve(Wp, bt[t_, Pp]) if t_ > 0 else torch.zeros(0, dtype=torch.float64, device="cuda")
+            rr = (bt[t_, cand] - cc @ bt[:t_, :][:, cand]).abs().cpu().numpy()
+            first_diff = {"step": t_ + 1, "row_blocked": int(idx[t_]), "row_streaming": int(idx_s[t_]),
+                          "residual_blocked_row": float(rr[0]), "residual_streaming_row": float(rr[1]),
+                          "relative_gap": float(abs(rr[0] - rr[1]) / max(rr[0], rr[1])),
+                          "cond_PtU": float(torch.linalg.cond(Wp).item()) if t_ > 0 else 1.0}
+        except Exception as ex:                 # diagnostics only: never lose the bench line over it
+            first_diff = {"error": repr(ex)}
     # DEIM through the host-pointer entry point (what the Julia shim calls), pinned host basis
     deim_e2e = None
     Bh = C.c_void_p()
@@ -538,7 +559,11 @@ def run_ours(args):
                 "achieved": panel_bytes / (deim_panel_ms * 1e-3) * 1e-9 if deim_panel_ms > 0 else None,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                 "frac": panel_bytes / (deim_panel_ms * 1e-3) * 1e-9 / hbm_peak if deim_panel_ms > 0 else None,
-                "live_read_peak_gbs": pk_g.value, "traffic": None,
+                "live_read_peak_gbs": pk_g.value,
+                # ncu --set full of the l0 = 128 panel launch at 16,777,216 rows: 19.327 GB read + 2.140 GB written
+                # for 21.475 GB algorithmic (profiles/r01_ncu_deim_blocked.txt): 1.000 x, summed over the launches
+                "traffic": 1.000 * panel_bytes,
+                "traffic_note": "ncu-measured 1.000 x algorithmic bytes (one launch), applied to all panel launches",
                 "bytes_per_rank": panel_bytes, "kernel_ms": deim_panel_ms,
                 "in_block_steps": {"kernel": "deim_step4_kernel (sub-panels of 4 columns) + deim_step_kernel inside the 16-column residual panel (k launches)",
                                    "bytes_per_rank": inblock_bytes, "kernel_ms": deim_step_ms,
@@ -557,7 +582,10 @@ def run_ours(args):
                         "ms": control_ms, "distinct_indices": len(set(idx_c.tolist()))},
             "roofline": roof,
             "streaming": {"ms": stream_ms, "algorithmic_gbs": deim_bytes(Md, kd) / (stream_ms * 1e-3) * 1e-9,
-                          "same_indices_as_blocked": bool(np.array_equal(idx_s, idx)), "roofline": stream_roof},
+                          "same_indices_as_blocked": bool(np.array_equal(idx_s, idx)),
+                          "positions_differing": int(np.sum(idx_s != idx)),
+                          "first_difference": first_diff,
+                          "roofline": stream_roof},
             "tail_ms": dacc["deim_tail"] / args.steps, "e2e": deim_e2e}
     B.free()
     if world > 1:

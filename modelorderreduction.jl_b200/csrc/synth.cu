@@ -99,8 +99,11 @@ struct BurgersCoef {
 };
 
 static void burgers_states(uint64_t seed, double p[3], double q[3], double d[3]) {
-    // generic (not grid-commensurate) front directions: no two grid nodes see bit-identical histories
-    const double P[3] = {0.9371, 0.0283, -0.7619}, Q[3] = {0.2517, -0.5139, 0.4877}, D[3] = {0.0, -0.45, -0.55};
+    // irrational front directions (correctly rounded square roots, the same doubles as in the oracle): with
+    // few-digit decimals the front normals are commensurate with a 4096-wide grid, distant nodes along a front
+    // then see histories equal to the last bit or two and the DEIM argmax is decided by rounding noise
+    const double P[3] = {sqrt(0.878), sqrt(0.0008), -sqrt(0.5805)}, Q[3] = {sqrt(0.0633), -sqrt(0.2641), sqrt(0.2379)};
+    const double D[3] = {0.0, -0.45, -0.55};
     for (int i = 0; i < 3; ++i) {
         p[i] = P[i];
         q[i] = Q[i];

@@ -356,7 +356,12 @@ def subspace_sine(U_ref: Array, U: Array) -> float:
 # --------------------------------------------------------------------------------------
 def burgers_states(seed: int = 0):
     """States (p_i, q_i) and phase offsets d_i of the three-front Cole-Hopf solution."""
-    P, Q, D = (0.9371, 0.0283, -0.7619), (0.2517, -0.5139, 0.4877), (0.0, -0.45, -0.55)
+    # irrational directions (correctly rounded square roots, identical in C and numpy): with few-digit
+    # decimals the front normals are commensurate with a 4096-wide grid and distant nodes along a front see
+    # histories that agree to the last bit or two -- argmax ties decided by rounding noise
+    P = (math.sqrt(0.878), math.sqrt(0.0008), -math.sqrt(0.5805))
+    Q = (math.sqrt(0.0633), -math.sqrt(0.2641), math.sqrt(0.2379))
+    D = (0.0, -0.45, -0.55)
     d = [D[i] + (float(((seed * (2 * i + 3)) & (2**64 - 1)) & 63) - 32.0) / 3200.0 for i in range(3)]
     return np.array(P), np.array(Q), np.array(d)
 
