@@ -260,6 +260,8 @@ int32_t mor_b200_shutdown(void) {
         g_ctx.ingest_bytes = 0;
         if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
         g_ctx.copy_stream = nullptr;
+        if (g_ctx.aux_stream) cudaStreamDestroy(g_ctx.aux_stream);
+        g_ctx.aux_stream = nullptr;
         if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
         g_ctx.own_stream = nullptr;
         g_ctx.stream = nullptr;

@@ -18,6 +18,7 @@
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 
 #include "internal.h"
 
@@ -298,7 +299,7 @@ deim_sub_coef_kernel(const double* __restrict__ Zb, const double* __restrict__ U
 __global__ void __launch_bounds__(1024)
 deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __restrict__ U, int64_t ld,
                   int64_t row_offset, int k, double* __restrict__ send, const double* __restrict__ Pn,
-                  int64_t ldp, int bw, const double* __restrict__ P2, int64_t ld2, int sw) {
+                  int64_t ldp, int bw, const double* __restrict__ P2, int64_t ld2, int sw, int kcols) {
     __shared__ double sv[32];
     __shared__ long long si[32];
     __shared__ long long widx;
@@ -321,7 +322,7 @@ deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __res
     __syncthreads();
     const long long g = widx;
     for (int j = threadIdx.x; j < k; j += 1024)
-        send[2 + j] = (g == MOR_IDX_NONE) ? 0.0 : U[(g - row_offset) + (int64_t)j * ld];
+        send[2 + j] = (g == MOR_IDX_NONE || j >= kcols) ? 0.0 : U[(g - row_offset) + (int64_t)j * ld];   // later columns: deferred
     if (Pn != nullptr && threadIdx.x < DEIM_BLOCK)
         send[2 + k + threadIdx.x] =
             (g == MOR_IDX_NONE || (int)threadIdx.x >= bw) ? 0.0 : Pn[(g - row_offset) + (int64_t)threadIdx.x * ldp];
@@ -350,6 +351,7 @@ struct UpdState {
     int i, k;                            // step (row being appended) and dimension of this state
     int rowoff;                          // offset of this state's row inside a gathered record
     int last;                            // 1: the final greedy step (a zero pivot no longer matters)
+    int jmax;                            // U-factor row i is formed for columns [i, jmax) (k unless later columns are deferred)
 };
 struct UpdArgs {
     UpdState st[2];                      // blockIdx.x selects: 0 = P'U of the basis, 1 = P'R of the current panel
@@ -425,12 +427,12 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
     {
         const int j = i + x;
         double s = 0.0;
-        if (active && j < k) {
+        if (active && j < S.jmax) {
 #pragma unroll 8
             for (int t = yy; t < i; t += ways) s = fma(ell[t], __ldcg(&Uf[(size_t)t * k + j]), s);
         }
         s = combine(s);
-        if (yy == 0 && j < k) Uf[(size_t)i * k + j] = w[j] - s;
+        if (yy == 0 && j < S.jmax) Uf[(size_t)i * k + j] = w[j] - s;
     }
     __syncthreads();
     for (int t = tid; t < i; t += 1024) ucol[t] = Uf[(size_t)t * k + i];
@@ -451,7 +453,7 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
             Zt[(size_t)i * k + x] = z;
         }
     }
-    if (i + 1 >= k) return;
+    if (i + 1 >= S.jmax) return;
     __syncthreads();
     for (int t = tid; t <= i; t += 1024) y[t] = Uf[(size_t)t * k + i + 1];
     __syncthreads();
@@ -464,6 +466,35 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
         }
         s = combine(s);
         if (yy == 0 && x <= i) c[x] = s;
+    }
+}
+
+// Deferred columns (pipelined host ingest: the basis arrives 16 columns at a time, so the rows of the points
+// chosen so far cannot be gathered beyond the columns that have landed).  At the panel boundary l1:
+//   deim_gather_block_kernel   W12[t][q] = U[idx[t], l1 + q], t < l1 (zero for rows of other ranks; all-reduced)
+//   deim_fwd_subst_kernel      Uf[0:l1, l1 + q] = inv(L[0:l1, 0:l1]) * W12[:, q]  (unit lower L, one warp per column q)
+// which is what the per-step bordered update would have left in those columns of the U-factor.
+__global__ void __launch_bounds__(128)
+deim_gather_block_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset,
+                         const long long* __restrict__ idx, int l1, int bw, double* __restrict__ W12) {
+    const int t = blockIdx.x * 8 + threadIdx.x / DEIM_BLOCK, q = threadIdx.x % DEIM_BLOCK;
+    if (t >= l1) return;
+    const long long loc = idx[t] - 1 - row_offset;
+    W12[t * DEIM_BLOCK + q] = (loc >= 0 && loc < m && q < bw) ? U[loc + (int64_t)(l1 + q) * ld] : 0.0;
+}
+
+__global__ void __launch_bounds__(32 * DEIM_BLOCK)
+deim_fwd_subst_kernel(const double* __restrict__ Lm, const double* __restrict__ W12, int k, int l1, int bw,
+                      double* Uf) {
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= bw) return;
+    double* y = Uf + l1 + q;                      // y[t * k] = Uf[t][l1 + q]
+    for (int t = 0; t < l1; ++t) {
+        double s = 0.0;
+        for (int r = lane; r < t; r += 32) s = fma(__ldcg(&Lm[(size_t)t * k + r]), __ldcg(&y[(size_t)r * k]), s);
+        s = warp_sum(s);
+        if (lane == 0) y[(size_t)t * k] = W12[t * DEIM_BLOCK + q] - s;
+        __syncwarp();
     }
 }
 
@@ -496,7 +527,8 @@ static bool deim_blocked_enabled() {
     return !(e && e[0] == '0');
 }
 
-int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host) {
+int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host,
+                            const cudaEvent_t* col_ready, int group_cols) {
     Ctx& cx = ctx();
     MOR_ARG(B != nullptr && idx_host != nullptr, "deim_interpolation_indices: null pointer");
     MOR_ARG(k >= 1 && k <= 1024, "deim_interpolation_indices: number of basis columns must be in 1..1024");
@@ -546,7 +578,7 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     // block state 5 * 16*16 + 16, sub-block state 5 * 4*4 + 4, sub-panel coefficients D 16 x 4
     const size_t bdoubles = 5 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK + 5 * DEIM_SUB * DEIM_SUB + DEIM_SUB +
                             DEIM_BLOCK * DEIM_SUB;
-    const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
+    const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20 + (size_t)k * DEIM_BLOCK;
     MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k + bdoubles + cp_doubles) + sizeof(long long) * k + 16));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
     // one record slot per greedy step: the update of the k x k factors (blocked path: on the side stream) may
@@ -568,6 +600,12 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* sst = bst + 5 * bb + DEIM_BLOCK;        // sub-block state
     double* Dsub = sst + 5 * ss + DEIM_SUB;         // sub-panel coefficients
     double* R2 = blocked && m > 0 ? panel.as<double>() + (size_t)ldp * DEIM_BLOCK : nullptr;
+    double* W12 = Cp + (cp_doubles - (size_t)k * DEIM_BLOCK);   // deferred columns of the chosen rows (k x 16)
+    // pipelined ingest: later columns of the basis are not there yet, so the k x k update is confined to the
+    // columns of the current panel and the rest is caught up at each panel boundary
+    const bool defer = blocked && col_ready != nullptr;
+    if (!blocked && col_ready != nullptr)
+        for (int g = 0; g * group_cols < (int)k; ++g) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[g], 0));
     // Blocked path: inside a block only the 16 x 16 factors of the panel decide the next coefficients, so the
     // (much longer) bordered update of the k x k factors runs on a side stream, off the per-step latency chain;
     // the main stream joins it at the next block boundary, where the panel coefficients need Z and Uf.
@@ -598,10 +636,19 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         const int64_t ld2 = (blocked && s0 > 0) ? ldp : ldn;
         double* send = xfer.as<double>() + (blocked ? slot * (size_t)i : 0);
         double* gathered = cx.nranks > 1 ? send + rec : send;
+        // pipelined host ingest: columns [i, i + group_cols) are first touched by this step (the panel of a
+        // block reads columns < l0 + 16 and DEIM_BLOCK == group_cols; the streaming step i reads columns <= i)
+        if (defer && i % group_cols == 0) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[i / group_cols], 0));
         if (blocked && j == 0 && l0 > 0) {
             MOR_CUDA(cudaEventRecord(ev_side, side));           // all earlier updates of the k x k factors
             MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
             t_panel.start();
+            if (defer) {
+                deim_gather_block_kernel<<<(l0 + 7) / 8, 128, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, W12);
+                if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W12, (size_t)l0 * DEIM_BLOCK));
+                deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
+                count_launch(2);
+            }
             deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
             count_launch();
             if (m > 0) MOR_TRY(deim_panel(B, ld, l0, bw, Cp, m, panel.as<double>(), ldp));
@@ -625,10 +672,11 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         t_step.stop();
         t_tail.start();
         deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send,
-                                                     blocked ? Pn : nullptr, ldn, bw, blocked ? P2 : nullptr, ld2, sw);
+                                                     blocked ? Pn : nullptr, ldn, bw, blocked ? P2 : nullptr, ld2, sw,
+                                                     defer ? l0 + bw : (int)k);
         if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)rec));
         UpdArgs ua;
-        ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0};
+        ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0, defer ? l0 + bw : (int)k};
         ua.st[1] = ua.st[0];
         if (blocked) {
             MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));       // record i is complete
@@ -636,9 +684,9 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
             deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
             UpdArgs ub;   // the panel's 16 x 16 factors and the sub-panel's 4 x 4 factors: two CTAs of one launch
             ub.st[0] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
-                                2 + (int)k, 1};
+                                2 + (int)k, 1, bw};
             ub.st[1] = UpdState{sst, sst + ss, sst + 2 * ss, sst + 3 * ss, sst + 4 * ss, sst + 5 * ss, nullptr, jj, sw,
-                                2 + (int)k + DEIM_BLOCK, 1};
+                                2 + (int)k + DEIM_BLOCK, 1, sw};
             deim_update_kernel<<<2, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
             count_launch(4);
         } else {
@@ -765,10 +813,42 @@ int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb
     MOR_ARG(B != nullptr && idx_out != nullptr, "mor_b200_deim_indices: null pointer");
     MOR_ARG(m >= 0 && k >= 1 && ldb >= (m > 0 ? m : 1), "mor_b200_deim_indices: bad dimensions");
     MOR_TRY(require_ctx());
+    Ctx& cx = ctx();
     mor_mat_t d = nullptr;
     MOR_TRY(mor_b200_mat_alloc(m, k, &d));
-    int32_t st = mor_b200_mat_upload(d, B, ldb);
-    if (st == MOR_OK) st = deim_indices_device(d->p, d->m, d->n, d->ld, idx_out);
+    // Pipelined ingest: the basis travels in groups of 16 columns on an upload stream; the greedy loop touches
+    // columns left to right (a panel needs the columns up to its own), so it starts on group 0 while the rest is
+    // still on the PCIe link -- the 34 GB of a 16M x 256 basis hide all but the last panel of the computation.
+    constexpr int GROUP = DEIM_BLOCK;
+    const int ngroups = (int)((k + GROUP - 1) / GROUP);
+    std::vector<cudaEvent_t> ev((size_t)ngroups + 2, nullptr);   // [ngroups] = start of the upload, [ngroups+1] = pad memset done
+    int32_t st = MOR_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (st == MOR_OK && e != cudaSuccess) st = cuda_fail(e, what, __FILE__, __LINE__);
+    };
+    if (!cx.aux_stream) cu(cudaStreamCreateWithFlags(&cx.aux_stream, cudaStreamNonBlocking), "cudaStreamCreate(aux)");
+    for (auto& e : ev) cu(cudaEventCreate(&e), "cudaEventCreate");
+    if (st == MOR_OK) {
+        cu(cudaEventRecord(ev[(size_t)ngroups + 1], cx.stream), "cudaEventRecord");   // mat_alloc zeroes the pad row on cx.stream
+        cu(cudaStreamWaitEvent(cx.aux_stream, ev[(size_t)ngroups + 1], 0), "cudaStreamWaitEvent");
+        cu(cudaEventRecord(ev[(size_t)ngroups], cx.aux_stream), "cudaEventRecord");
+        for (int g = 0; g < ngroups && st == MOR_OK; ++g) {
+            const int64_t c0 = (int64_t)g * GROUP, nc = k - c0 < GROUP ? k - c0 : GROUP;
+            if (m > 0)
+                cu(cudaMemcpy2DAsync(d->p + (size_t)c0 * d->ld, (size_t)d->ld * 8, B + (size_t)c0 * ldb, (size_t)ldb * 8,
+                                     (size_t)m * 8, (size_t)nc, cudaMemcpyHostToDevice, cx.aux_stream),
+                   "cudaMemcpy2DAsync(basis columns)");
+            cu(cudaEventRecord(ev[(size_t)g], cx.aux_stream), "cudaEventRecord");
+        }
+    }
+    if (st == MOR_OK) st = deim_indices_device(d->p, d->m, d->n, d->ld, idx_out, ev.data(), GROUP);
+    if (cx.aux_stream) cudaStreamSynchronize(cx.aux_stream);     // nothing may still read the caller's buffer
+    if (st == MOR_OK) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[(size_t)ngroups], ev[(size_t)ngroups - 1]) == cudaSuccess) cx.timings[MOR_T_H2D] = ms;
+    }
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
     mor_b200_mat_free(d);
     return st;
 }

@@ -40,7 +40,8 @@ struct Ctx {
     int num_sms = 148;
     cudaStream_t stream = nullptr;      // the stream all work is enqueued on
     cudaStream_t own_stream = nullptr;  // created by init
-    cudaStream_t copy_stream = nullptr; // host->device ingest, overlapped with the first Gram pass
+    cudaStream_t copy_stream = nullptr; // host->device ingest, overlapped with the first Gram pass; DEIM side stream
+    cudaStream_t aux_stream = nullptr;  // DEIM host ingest: column groups upload while earlier panels are processed
     void* comm = nullptr;               // ncclComm_t
     int rank = 0, nranks = 1;
     double timings[MOR_T_NSLOTS] = {0};
@@ -131,7 +132,10 @@ int32_t kat_check_left(const double* U, int64_t m, int64_t ld, int k, int64_t n,
                        double decades, double* max_err);
 
 // ---- DEIM (deim.cu) -------------------------------------------------------------------------
-int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host);
+// col_ready (optional): event g is recorded once columns [g * group_cols, (g + 1) * group_cols) of B are in place
+// (pipelined host ingest); the greedy loop waits for group g right before it first touches those columns.
+int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host,
+                            const cudaEvent_t* col_ready = nullptr, int group_cols = 16);
 // R (m x bw, ldr) = U[:, l0 : l0+bw] - U[:, 0 : l0] * C with C packed in 16-row slabs (deim_panel.cu)
 int32_t deim_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp, int64_t m, double* R, int64_t ldr);
 
