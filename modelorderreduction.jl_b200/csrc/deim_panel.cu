@@ -6,9 +6,9 @@
 //
 // Design (B200): HBM-bound -- 8 m (l0 + bw) bytes read, 8 m bw written, 2 m l0 bw flop (4 flop/B at
 // bw = 16, below the FP64 tensor balance of ~5.3).  Persistent CTAs (one per SM) walk row tiles; a
-// producer warp streams, through a 6-stage mbarrier ring that runs ahead across tile boundaries, KC
-// 1-D bulk copies per stage (KC basis columns x RT rows, RT * KC = 2048 doubles; default 256 rows x 8
-// columns = 2 KB contiguous runs; shared row stride RT + 4 doubles) plus the matching 16 x 16 slab of C
+// producer warp streams, through an NS-stage mbarrier ring that runs ahead across tile boundaries, KC
+// 1-D bulk copies per stage (KC basis columns x RT rows; default 256 rows x 16 columns = 2 KB contiguous
+// runs, 32 KB per stage, 5 stages; shared row stride RT + 4 doubles) plus the matching 16 x 16 slab of C
 // (stride 20), both = 4 (mod 16) eight-byte banks: conflict-free DMMA.8x8x4 fragment loads.  The last
 // stages of every tile carry the bw columns U[:, l0 : l0+bw] themselves, so the epilogue (subtract, store)
 // also reads from shared memory.  Eight consumer warps own RT / 8 rows x 16 columns each.
@@ -23,28 +23,27 @@ namespace {
 constexpr int PN_BW = 16;       // panel width = columns per C slab
 constexpr int PN_CS = 20;       // shared C slab stride (doubles)
 constexpr int PN_SLAB = PN_BW * PN_CS;        // 320 doubles
-constexpr int PN_STAGES = 6;
 constexpr int PN_WARPS = 8;
 constexpr int PN_THREADS = PN_WARPS * 32 + 32;
 
 // RT rows per tile x KC basis columns per stage (RT * KC = 2048 doubles = 16 KB of basis per stage):
 // a stage is KC bulk copies of RT * 8 contiguous bytes each -- the longer the run, the fewer DRAM pages
 // a stage touches.
-template <int RT, int KC>
+template <int RT, int KC, int NS>
 struct PanelCfg {
     static constexpr int RS = RT + 4;               // shared row-tile stride (doubles), = 4 (mod 16) banks
     static constexpr int XS = KC * RS;
     static constexpr int STAGE = XS + PN_SLAB;      // doubles
     static constexpr int MI = RT / (8 * PN_WARPS);  // 8-row DMMA tiles per warp
-    static constexpr size_t SMEM = (size_t)PN_STAGES * STAGE * 8 + 2 * PN_STAGES * 8 + 128;
+    static constexpr size_t SMEM = (size_t)NS * STAGE * 8 + 2 * NS * 8 + 128;
 };
 
-template <int RT, int KC>
+template <int RT, int KC, int NS>
 __global__ void __launch_bounds__(PN_THREADS, 1)
 deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, const double* __restrict__ Cp,
                   long long m, double* __restrict__ R, long long ldr) {
-    using Cfg = PanelCfg<RT, KC>;
-    constexpr int RS = Cfg::RS, XS = Cfg::XS, STAGE = Cfg::STAGE, MI = Cfg::MI;
+    using Cfg = PanelCfg<RT, KC, NS>;
+    constexpr int RS = Cfg::RS, XS = Cfg::XS, STAGE = Cfg::STAGE, MI = Cfg::MI, PN_STAGES = NS;
     extern __shared__ unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)PN_STAGES * STAGE);
@@ -162,19 +161,19 @@ deim_panel_kernel(const double* __restrict__ U, long long ld, int l0, int bw, co
     }
 }
 
-template <int RT, int KC>
+template <int RT, int KC, int NS>
 int32_t launch_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp, int64_t m, double* R, int64_t ldr) {
-    using Cfg = PanelCfg<RT, KC>;
+    using Cfg = PanelCfg<RT, KC, NS>;
     Ctx& cx = ctx();
     static bool attr_set = false;
     if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel<RT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel<RT, KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)Cfg::SMEM));
         attr_set = true;
     }
     const int64_t tiles = (m + RT - 1) / RT;
     const int grid = (int)(tiles < (int64_t)cx.num_sms ? tiles : (int64_t)cx.num_sms);
-    deim_panel_kernel<RT, KC><<<grid, PN_THREADS, Cfg::SMEM, cx.stream>>>(U, ld, l0, bw, Cp, m, R, ldr);
+    deim_panel_kernel<RT, KC, NS><<<grid, PN_THREADS, Cfg::SMEM, cx.stream>>>(U, ld, l0, bw, Cp, m, R, ldr);
     MOR_CUDA(cudaGetLastError());
     count_launch();
     return MOR_OK;
@@ -190,14 +189,18 @@ int32_t deim_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp
     MOR_ARG(ld % 2 == 0 && (uintptr_t)U % 16 == 0 && ld >= ((m + 1) & ~int64_t(1)),
             "deim_panel: the basis must be 16-byte aligned with an even leading dimension >= m rounded up to even");
     if (m == 0) return MOR_OK;
-    // Tile shape, measured at 16M x 256 on B200 (sum of the 15 panel launches, 322 GB of traffic):
-    // 128 x 16 (1 KB runs) 82.4 ms, 256 x 8 (2 KB runs) 54.6 ms = 5.9 TB/s, 512 x 4 (4 KB runs, one k-step
-    // per stage) 73.2 ms.  MOR_B200_PANEL_TILE selects the other shapes (tests, experiments).
+    // Tile shape (rows x columns per stage, stages), measured at 16M x 256 on B200 as the sum of the 15 panel
+    // launches (322 GB of traffic): 128 x 16 x 6 (1 KB runs) 82.4 ms; 256 x 8 x 6 (2 KB runs) 54.5 ms; 256 x 8 x 8
+    // 53.5; 256 x 8 x 10 54.4; 512 x 4 x 6 (4 KB runs, one k-step per stage) 73.2; 256 x 16 x 5 (2 KB runs, 32 KB
+    // stages) 52.1 ms = 6.18 TB/s -- the default.  MOR_B200_PANEL_TILE selects the others (tests, experiments).
     const char* v = getenv("MOR_B200_PANEL_TILE");
-    const int rt = v ? atoi(v) : 256;
-    if (rt == 512) return launch_panel<512, 4>(U, ld, l0, bw, Cp, m, R, ldr);
-    if (rt == 128) return launch_panel<128, 16>(U, ld, l0, bw, Cp, m, R, ldr);
-    return launch_panel<256, 8>(U, ld, l0, bw, Cp, m, R, ldr);
+    const int rt = v ? atoi(v) : 25616;
+    if (rt == 512) return launch_panel<512, 4, 6>(U, ld, l0, bw, Cp, m, R, ldr);
+    if (rt == 128) return launch_panel<128, 16, 6>(U, ld, l0, bw, Cp, m, R, ldr);
+    if (rt == 256) return launch_panel<256, 8, 6>(U, ld, l0, bw, Cp, m, R, ldr);
+    if (rt == 2568) return launch_panel<256, 8, 8>(U, ld, l0, bw, Cp, m, R, ldr);
+    if (rt == 25610) return launch_panel<256, 8, 10>(U, ld, l0, bw, Cp, m, R, ldr);
+    return launch_panel<256, 16, 5>(U, ld, l0, bw, Cp, m, R, ldr);
 }
 
 }  // namespace mor

@@ -125,10 +125,10 @@ def test_jacobi_svd(gpu, rows, n, kappa):
 
 @pytest.mark.parametrize("m,l0,bw", [(1, 16, 16), (127, 16, 3), (128, 32, 16), (129, 48, 16), (4099, 240, 16),
                                      (50_001, 112, 9), (300_000, 64, 16)])
-@pytest.mark.parametrize("tile", [128, 256, 512])
+@pytest.mark.parametrize("tile", [128, 256, 512, 25616])
 def test_deim_panel_residual(gpu, monkeypatch, m, l0, bw, tile):
     """deim_panel_kernel: R = U[:, l0:l0+bw] - U[:, :l0] C (the residual panel of the blocked DEIM path),
-    for every tile shape of the kernel (rows per tile x columns per stage = 128x16, 256x8, 512x4)."""
+    for every tile shape of the kernel (rows per tile x columns per stage = 128x16, 256x8, 512x4, default 256x16)."""
     monkeypatch.setenv("MOR_B200_PANEL_TILE", str(tile))
     rng = np.random.default_rng(m + l0 + bw)
     U = rng.standard_normal((m, l0 + bw)); Cm = rng.standard_normal((l0, bw))
