@@ -310,6 +310,64 @@ def deim_interpolation_indices_sharded(local_basis: Array, row_offset: int, allg
     return indices + 1
 
 
+class _BorderedLU:
+    """LU factors of the growing square pivot block W = P'U kept the way the library keeps them
+    (csrc/deim.cu:deim_update_kernel): W = L * Uf with unit lower L, Z = inv(Uf) explicit; row i is
+    appended by a bordered (Doolittle) update -- the greedy choice is partial pivoting, so no row
+    exchanges are needed.  ``c`` holds the coefficients of the next column."""
+
+    def __init__(self, k: int):
+        self.k = k
+        self.Uf, self.L, self.Z, self.c = np.zeros((k, k)), np.zeros((k, k)), np.zeros((k, k)), np.zeros(k)
+
+    def append(self, i: int, w: Array) -> None:
+        k = self.k
+        ell = np.array([w[:j + 1] @ self.Z[:j + 1, j] for j in range(i)])
+        self.L[i, :i] = ell
+        self.Uf[i, i:] = w[i:] - ell @ self.Uf[:i, i:]
+        piv = self.Uf[i, i]
+        if piv == 0.0 and i < k - 1:
+            raise np.linalg.LinAlgError("SingularException")
+        for r in range(i):
+            self.Z[r, i] = -(self.Z[r, r:i] @ self.Uf[r:i, i]) / piv
+        self.Z[i, i] = 1.0 / piv
+        if i + 1 < k:
+            self.c[:i + 1] = np.triu(self.Z[:i + 1, :i + 1]) @ self.Uf[:i + 1, i + 1]
+
+    def coefficients(self, l: int, cols: slice) -> Array:
+        """inv(W[:l, :l]) @ W[:l, cols] for later columns (their inv(L)-part is already in Uf)."""
+        return np.triu(self.Z[:l, :l]) @ self.Uf[:l, cols]
+
+
+def deim_interpolation_indices_blocked(basis: Array, block: int = 16, sub: int = 4) -> Array:
+    """The library's blocked DEIM (csrc/deim.cu, csrc/deim_panel.cu) restated in numpy: the residual
+    r_l = u_l - U_{l-1} inv(P'U_{l-1}) P'u_l of deim.jl:21-23 is column l of the Schur complement of an
+    LU factorisation of the tall basis with the interpolation rows as pivots, so it can be formed panel
+    by panel:  P1 = U[:, l0:l0+block] - U[:, :l0] C  (one pass over the first l0 columns per panel),
+    P2 = P1[:, s0:s0+sub] - P1[:, :s0] D inside a panel, and the greedy steps of deim.jl:24 inside a
+    sub-panel.  Same indices as :func:`deim_interpolation_indices` (tests/test_oracle.py)."""
+    U = np.asarray(basis, dtype=np.float64)
+    m, k = U.shape
+    G = _BorderedLU(k)
+    idx = []
+    for l0 in range(0, k, block):
+        bw = min(block, k - l0)
+        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ G.coefficients(l0, slice(l0, l0 + bw))
+        S1 = _BorderedLU(bw)
+        for s0 in range(0, bw, sub):
+            sw = min(sub, bw - s0)
+            P2 = P1[:, :sw] if s0 == 0 else P1[:, s0:s0 + sw] - P1[:, :s0] @ S1.coefficients(s0, slice(s0, s0 + sw))
+            S2 = _BorderedLU(sw)
+            for jj in range(sw):
+                r = np.abs(P2[:, jj] - P2[:, :jj] @ S2.c[:jj]) if jj else np.abs(P2[:, 0])
+                p = argmax_first(r)
+                idx.append(p)
+                G.append(l0 + s0 + jj, U[p, :].copy())
+                S1.append(s0 + jj, P1[p, :].copy())
+                S2.append(jj, P2[p, :].copy())
+    return np.array(idx, dtype=np.int64) + 1
+
+
 def pod_svd_sharded(local_X: Array, allreduce_sum) -> Tuple[Array, Array]:
     """Row-sharded POD factorisation as the library performs it (CholeskyQR2 + SVD of the
     small factor): partial Gram matrices are summed across shards, everything n x n is

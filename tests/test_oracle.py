@@ -183,3 +183,26 @@ def test_burgers_snapshots_layout_and_shard_invariance():
     # the fronts travel: snapshots are linearly independent (slow singular value decay)
     s = sla.svd(X, compute_uv=False)
     assert s[-1] / s[0] > 1e-6
+
+
+def test_blocked_deim_restatement_equals_the_reference_formulation(golden):
+    """The blocked left-looking-LU form of DEIM that the library runs (panels of 16, sub-panels of 4) picks the
+    same points as deim.jl:9-28 restated line for line -- on the golden cases, the sin fixture, exact ties,
+    the singular fixture and the Burgers POD basis."""
+    for case in golden["deim_random"]:
+        rng = np.random.Generator(np.random.PCG64(case["seed"]))
+        Q, _ = np.linalg.qr(rng.standard_normal((case["m"], case["k"])))
+        assert O.deim_interpolation_indices_blocked(Q).tolist() == case["indices"]
+        assert O.deim_interpolation_indices_blocked(Q, block=8, sub=2).tolist() == case["indices"]
+    U, _, _ = O._svd(sin_fixture())
+    assert O.deim_interpolation_indices_blocked(U, block=4, sub=2).tolist() == golden["F2"]["deim_U10"]
+    rng = np.random.Generator(np.random.PCG64(77))
+    A = rng.standard_normal((3000, 40)); A[2000:3000] = A[500:1500]          # exact ties: the lower index wins
+    want = O.deim_interpolation_indices(A)
+    assert O.deim_interpolation_indices_blocked(A).tolist() == want.tolist() and not np.any(want > 2000)
+    Z = np.zeros((4, 3)); Z[:, 1] = 1; Z[:, 2] = [1, 2, 3, 4]
+    with pytest.raises(np.linalg.LinAlgError):
+        O.deim_interpolation_indices_blocked(Z)
+    S = O.burgers_snapshots(96 * 96, 40, 96, 2e-3, seed=1)
+    Ub = O._svd(S)[0]
+    assert O.deim_interpolation_indices_blocked(Ub).tolist() == O.deim_interpolation_indices(Ub).tolist()
