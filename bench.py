@@ -3,8 +3,11 @@
 
   POD `reduce!(pod, SVD())` of the synthetic 16,777,216 x 1024 FP64 snapshot matrix (k = 64),
   rows sharded over the N ranks (strong scaling), reported as algorithmic FP64 TFLOP/s
-  (2mn^2 + 2mnk flop) and ms; plus DEIM `deim_interpolation_indices` on a
-  16,777,216 x 256 orthonormal basis as ms and algorithmic HBM GB/s (4mk(k+1) bytes).
+  (2mn^2 + 2mnk flop) and ms; plus DEIM `deim_interpolation_indices` on the
+  16,777,216 x 256 POD basis of 2-D Burgers snapshots (BASELINE config 5; generated and POD'd on the
+  device) as ms and algorithmic HBM GB/s (4mk(k+1) bytes, the reference formulation's traffic), with
+  the default blocked path, the streaming path (MOR_B200_DEIM_BLOCK=0) and a Philox control basis
+  side by side, each kernel against the HBM roofline on the bytes it actually moves.
 
 One "step" = one full pass of the hot path over the resident input: factorisation
 (Gram -> Cholesky -> Jacobi) + basis U_k.  `value` is device-resident (inputs in HBM when the
