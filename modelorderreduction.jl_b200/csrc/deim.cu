@@ -569,6 +569,56 @@ deim_block_update_kernel(const double* __restrict__ slots, size_t slot_stride, i
     }
 }
 
+// EXPERIMENTAL (same switch): inv(L) kept explicitly (Li, unit lower, strictly lower part stored) so that the
+// deferred columns Y12 = inv(L11) W12 at a panel boundary are a parallel product instead of the sequential
+// deim_fwd_subst_kernel.  Per panel: Li22 = inv(L22) (16 x 16, every CTA redundantly), N = Li22 L21,
+// Li21 = -N Li11; CTA c owns row l0 + c.  Runs after deim_block_update_kernel (needs its L21 rows).
+__global__ void __launch_bounds__(256)
+deim_block_linv_kernel(int k, int l0, int bw, const double* __restrict__ Lmb, const double* __restrict__ Lm,
+                       double* Li) {
+    __shared__ double li22[DEIM_BLOCK * DEIM_BLOCK], nrow[1024];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (tid < bw) {   // column tid of inv(I + L22) by forward substitution
+        const int cc = tid;
+        for (int r = 0; r < bw; ++r) li22[r * DEIM_BLOCK + cc] = r == cc ? 1.0 : 0.0;
+        for (int r = cc + 1; r < bw; ++r) {
+            double a = 0.0;
+            for (int t = cc; t < r; ++t) a = fma(Lmb[r * bw + t], li22[t * DEIM_BLOCK + cc], a);
+            li22[r * DEIM_BLOCK + cc] = -a;
+        }
+    }
+    __syncthreads();
+    for (int x = tid; x < l0; x += 256) {
+        double a = 0.0;
+        for (int r = 0; r <= c; ++r) a = fma(li22[c * DEIM_BLOCK + r], Lm[(size_t)(l0 + r) * k + x], a);
+        nrow[x] = a;
+    }
+    __syncthreads();
+    for (int x = tid; x < l0; x += 256) {
+        double a = nrow[x];
+        for (int t = x + 1; t < l0; ++t) a = fma(nrow[t], __ldcg(&Li[(size_t)t * k + x]), a);
+        Li[(size_t)(l0 + c) * k + x] = -a;
+    }
+    if (tid < c) Li[(size_t)(l0 + c) * k + l0 + tid] = li22[c * DEIM_BLOCK + tid];
+}
+
+// Uf[t][l1 + q] = W12[t][q] + sum_{s < t} Li[t][s] * W12[s][q],  t < l1, q < bw     (Y12 = inv(L11) W12)
+__global__ void __launch_bounds__(256)
+deim_linv_apply_kernel(const double* __restrict__ Li, const double* __restrict__ W12, int k, int l1, int bw,
+                       double* __restrict__ Uf) {
+    const int t = blockIdx.x * DEIM_BLOCK + threadIdx.x / DEIM_BLOCK, q = threadIdx.x % DEIM_BLOCK;
+    if (t >= l1 || q >= bw) return;
+    double a0 = W12[t * DEIM_BLOCK + q], a1 = 0.0;
+    const double* li = Li + (size_t)t * k;
+    int sidx = 0;
+    for (; sidx + 2 <= t; sidx += 2) {
+        a0 = fma(li[sidx], W12[sidx * DEIM_BLOCK + q], a0);
+        a1 = fma(li[sidx + 1], W12[(sidx + 1) * DEIM_BLOCK + q], a1);
+    }
+    if (sidx < t) a0 = fma(li[sidx], W12[sidx * DEIM_BLOCK + q], a0);
+    Uf[(size_t)t * k + l1 + q] = a0 + a1;
+}
+
 // Coefficients of the next panel, packed for deim_panel_kernel: C = Z[0:l1, 0:l1] * Uf[0:l1, l1 : l1+bw]
 // (Uf[:, j] = inv(L) P'u_j is already part of the U-factor, Z = inv(Uf[0:l1, 0:l1])), i.e. column q of C
 // solves (P'U_l1) c = P'u_{l1+q}, deim.jl:21.  One CTA per 16-row slab: Cp[c][q][kk] = C[16 c + kk][q].
@@ -725,7 +775,10 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
             if (defer) {
                 deim_gather_block_kernel<<<(l0 + 7) / 8, 128, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, W12);
                 if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W12, (size_t)l0 * DEIM_BLOCK));
-                deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
+                if (blockupd)   // Wm is free in this mode (no per-step update of the k x k factors): it holds inv(L)
+                    deim_linv_apply_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(Wm, W12, (int)k, l0, bw, Uf);
+                else
+                    deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
                 count_launch(2);
             }
             deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
@@ -774,7 +827,8 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
                 deim_block_update_kernel<<<bw, 256, 0, cx.stream>>>(
                     xfer.as<double>() + slot * (size_t)l0, slot, cx.nranks, rec, (int)k, l0, bw, bst + bb, bst + 2 * bb,
                     bst + 3 * bb, Uf, Lm, Z, Zt, idx_d, l0 + bw >= (int)k ? 1 : 0, status_d);
-                count_launch();
+                deim_block_linv_kernel<<<bw, 256, 0, cx.stream>>>((int)k, l0, bw, bst + 2 * bb, Lm, Wm);
+                count_launch(2);
             }
         } else {
             deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
