@@ -368,6 +368,75 @@ def deim_interpolation_indices_blocked(basis: Array, block: int = 16, sub: int =
     return np.array(idx, dtype=np.int64) + 1
 
 
+def deim_interpolation_indices_blocked_sharded(local_basis: Array, row_offset: int, allgather, allreduce_sum,
+                                               block: int = 16, sub: int = 4, cols_ready=None) -> Array:
+    """The blocked DEIM over contiguous row shards, with the library's exchange steps: per greedy step one
+    all-gather of (value, global index, rows of the basis / panel / sub-panel at that index); with pipelined
+    ingest (``cols_ready(l)`` = number of basis columns that have landed when step l starts) the rows of the
+    chosen points are only gathered up to the current panel, and the later columns are caught up at each panel
+    boundary by gathering them from their owners (zeros elsewhere) and all-reducing -- csrc/deim.cu:
+    deim_gather_block_kernel / deim_fwd_subst_kernel.  Panels and sub-panels are local to each rank."""
+    U = np.asarray(local_basis, dtype=np.float64)
+    m, k = U.shape
+    G = _BorderedLU(k)
+    idx = []
+    defer = cols_ready is not None
+
+    def owned_rows(cols: slice) -> Array:
+        out = np.zeros((len(idx), cols.stop - cols.start))
+        for t, g in enumerate(idx):
+            if row_offset <= g < row_offset + m:
+                out[t] = U[g - row_offset, cols]
+        return allreduce_sum(out)
+
+    for l0 in range(0, k, block):
+        bw = min(block, k - l0)
+        if defer:
+            assert cols_ready(l0) >= l0 + bw, "a panel needs the columns up to its own"
+            if l0 > 0:                                   # catch up the deferred columns of the U-factor
+                W12 = owned_rows(slice(l0, l0 + bw))
+                Lfull = np.tril(G.L[:l0, :l0], -1) + np.eye(l0)
+                G.Uf[:l0, l0:l0 + bw] = sla.solve_triangular(Lfull, W12, lower=True, unit_diagonal=True)
+        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ G.coefficients(l0, slice(l0, l0 + bw))
+        S1 = _BorderedLU(bw)
+        for s0 in range(0, bw, sub):
+            sw = min(sub, bw - s0)
+            P2 = P1[:, :sw] if s0 == 0 else P1[:, s0:s0 + sw] - P1[:, :s0] @ S1.coefficients(s0, slice(s0, s0 + sw))
+            S2 = _BorderedLU(sw)
+            for jj in range(sw):
+                r = np.abs(P2[:, jj] - P2[:, :jj] @ S2.c[:jj]) if jj else np.abs(P2[:, 0])
+                if r.size:
+                    p = argmax_first(r)
+                    urow = U[p, :].copy()
+                    if defer:
+                        urow[l0 + bw:] = 0.0             # those columns are still on the PCIe link
+                    cand = (float(r[p]), row_offset + p, urow, P1[p, :].copy(), P2[p, :].copy())
+                else:
+                    cand = (-1.0, -1, np.zeros(k), np.zeros(bw), np.zeros(sw))
+                best = None
+                for c in allgather(cand):
+                    if c[1] >= 0 and (best is None or _better(c[0], c[1], best[0], best[1])):
+                        best = c
+                idx.append(best[1])
+                i = l0 + s0 + jj
+                if defer:                                # bordered update confined to the panel's columns
+                    w = best[2]
+                    ell = np.array([w[:j + 1] @ G.Z[:j + 1, j] for j in range(i)])
+                    G.L[i, :i] = ell
+                    G.Uf[i, i:l0 + bw] = w[i:l0 + bw] - ell @ G.Uf[:i, i:l0 + bw]
+                    piv = G.Uf[i, i]
+                    if piv == 0.0 and i < k - 1:
+                        raise np.linalg.LinAlgError("SingularException")
+                    for rr in range(i):
+                        G.Z[rr, i] = -(G.Z[rr, rr:i] @ G.Uf[rr:i, i]) / piv
+                    G.Z[i, i] = 1.0 / piv
+                else:
+                    G.append(i, best[2])
+                S1.append(s0 + jj, best[3])
+                S2.append(jj, best[4])
+    return np.array(idx, dtype=np.int64) + 1
+
+
 def pod_svd_sharded(local_X: Array, allreduce_sum) -> Tuple[Array, Array]:
     """Row-sharded POD factorisation as the library performs it (CholeskyQR2 + SVD of the
     small factor): partial Gram matrices are summed across shards, everything n x n is
