@@ -232,9 +232,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- live roofline denominators (FP64 DMMA issue rate, streaming read) ----------------------
-    lib.mor_dbg_peaks.restype = C.c_int32
+    tlib = _lib.load_test()      # libmor_b200_test.so: peak probes and the plain gemm_tn hook used by the checks
+    tlib.mor_dbg_peaks.restype = C.c_int32
     pk_t, pk_g = C.c_double(0), C.c_double(0)
-    _lib.check(lib.mor_dbg_peaks(3, 4, C.byref(pk_t), C.byref(pk_g)))
+    _lib.check(tlib.mor_dbg_peaks(3, 4, C.byref(pk_t), C.byref(pk_g)))
     peaks_file = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -290,14 +291,14 @@ def run_ours(args):
     # (no CPU oracle fits 16M rows): U_k orthonormal; (sigma_i, u_i, v_i) are singular triplets of X
     # (X'U_k = V_k S_k); the full spectrum carries all the energy (sum sigma^2 = ||X||_F^2, the norm
     # computed independently by torch on the same device memory).
-    lib.mor_dbg_gemm_tn.restype = C.c_int32
+    tlib.mor_dbg_gemm_tn.restype = C.c_int32
     f = pod_factor_dev(X, _lib.MOR_SVD, k, m_global=M)
     f.basis(k, U)
     s = f.s
     Vk = f.right(k, DeviceMatrix.alloc(n, k)).to_host()
     UtU, XtU = DeviceMatrix.alloc(k, k), DeviceMatrix.alloc(n, k)
-    _lib.check(lib.mor_dbg_gemm_tn(U.handle, U.handle, UtU.handle))
-    _lib.check(lib.mor_dbg_gemm_tn(X.handle, U.handle, XtU.handle))
+    _lib.check(tlib.mor_dbg_gemm_tn(U.handle, U.handle, UtU.handle))
+    _lib.check(tlib.mor_dbg_gemm_tn(X.handle, U.handle, XtU.handle))
     g = torch.from_numpy(np.ascontiguousarray(UtU.to_host())).cuda()
     w = torch.from_numpy(np.ascontiguousarray(XtU.to_host())).cuda()
 
@@ -446,7 +447,7 @@ def run_ours(args):
     barrier()
     basis_pod_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     BtB = DeviceMatrix.alloc(kd, kd)
-    _lib.check(lib.mor_dbg_gemm_tn(B.handle, B.handle, BtB.handle))
+    _lib.check(tlib.mor_dbg_gemm_tn(B.handle, B.handle, BtB.handle))
     gb = torch.from_numpy(np.ascontiguousarray(BtB.to_host())).cuda()
     if world > 1:
         dist.all_reduce(gb)

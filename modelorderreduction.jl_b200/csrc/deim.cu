@@ -498,127 +498,6 @@ deim_fwd_subst_kernel(const double* __restrict__ Lm, const double* __restrict__ 
     }
 }
 
-// EXPERIMENTAL (MOR_B200_DEIM_BLOCKUPDATE=1, default off; not yet validated on hardware): one update of the
-// k x k factors per panel instead of one bordered update per greedy step.  With the panel's own factors
-// W22 - L21 Y12 = L22 U22, Z22 = inv(U22) (the 16 x 16 state kept for the in-panel steps) the extension is
-//   L21 = W21 Z11,   L = [L11 0; L21 L22],   Uf = [U11 Y12; 0 U22],   Z = [Z11  -Z11 Y12 Z22; 0  Z22]
-// (restated in numpy and checked against the reference formulation: see DESIGN.md section 8).  CTA c forms row c of
-// L21 and column c of Z12 and copies row / column c of the panel factors; `slots` are the gathered records of
-// the panel's greedy steps.
-__global__ void __launch_bounds__(256)
-deim_block_update_kernel(const double* __restrict__ slots, size_t slot_stride, int nranks, int rec, int k, int l0,
-                         int bw, const double* __restrict__ Ufb, const double* __restrict__ Lmb,
-                         const double* __restrict__ Zb, double* __restrict__ Uf, double* __restrict__ Lm,
-                         double* __restrict__ Z, double* __restrict__ Zt, long long* __restrict__ idx_out,
-                         int last_block, int* __restrict__ status) {
-    __shared__ double w[1024], tcol[1024];
-    __shared__ int win_s;
-    const int c = blockIdx.x, tid = threadIdx.x;
-    const double* gathered = slots + (size_t)c * slot_stride + (nranks > 1 ? rec : 0);
-    if (tid == 0) {
-        int win = 0;
-        double bv = -1.0;
-        long long bi = MOR_IDX_NONE;
-        for (int r = 0; r < nranks; ++r) {
-            const double v = gathered[(size_t)r * rec];
-            const long long ix = __double_as_longlong(gathered[(size_t)r * rec + 1]);
-            if (cand_better(v, ix, bv, bi)) {
-                bv = v;
-                bi = ix;
-                win = r;
-            }
-        }
-        win_s = win;
-        idx_out[l0 + c] = bi + 1;
-        const bool final_step = last_block && c == bw - 1;
-        if (Ufb[c * bw + c] == 0.0 && !final_step && *status == 0) *status = l0 + c + 1;
-    }
-    __syncthreads();
-    const double* src = gathered + (size_t)win_s * rec + 2;
-    for (int t = tid; t < l0; t += 256) w[t] = src[t];
-    // T[s] = (Y12 * Z22)[s][c] = sum_{q <= c} Uf[s][l0 + q] * Zb[q][c]
-    for (int sidx = tid; sidx < l0; sidx += 256) {
-        double a = 0.0;
-        for (int q = 0; q <= c; ++q) a = fma(Uf[(size_t)sidx * k + l0 + q], Zb[q * bw + c], a);
-        tcol[sidx] = a;
-    }
-    __syncthreads();
-    // L21 row c:  L[l0 + c][x] = sum_{t <= x} w[t] * Z[t][x]
-    for (int x = tid; x < l0; x += 256) {
-        double a = 0.0;
-        for (int t = 0; t <= x; ++t) a = fma(w[t], __ldcg(&Z[(size_t)t * k + x]), a);
-        Lm[(size_t)(l0 + c) * k + x] = a;
-    }
-    // Z12 column c:  Z[t][l0 + c] = -sum_{s >= t} Z[t][s] * T[s]   (read through Zt: coalesced over t)
-    for (int t = tid; t < l0; t += 256) {
-        double a = 0.0;
-        for (int sidx = t; sidx < l0; ++sidx) a = fma(__ldcg(&Zt[(size_t)sidx * k + t]), tcol[sidx], a);
-        Z[(size_t)t * k + l0 + c] = -a;
-        Zt[(size_t)(l0 + c) * k + t] = -a;
-    }
-    // row c of L22 / U22, column c of Z22
-    if (tid < bw) {
-        const int q = tid;
-        if (q < c) Lm[(size_t)(l0 + c) * k + l0 + q] = Lmb[c * bw + q];
-        if (q >= c) Uf[(size_t)(l0 + c) * k + l0 + q] = Ufb[c * bw + q];
-        if (q <= c) {
-            const double z = Zb[q * bw + c];
-            Z[(size_t)(l0 + q) * k + l0 + c] = z;
-            Zt[(size_t)(l0 + c) * k + l0 + q] = z;
-        }
-    }
-}
-
-// EXPERIMENTAL (same switch): inv(L) kept explicitly (Li, unit lower, strictly lower part stored) so that the
-// deferred columns Y12 = inv(L11) W12 at a panel boundary are a parallel product instead of the sequential
-// deim_fwd_subst_kernel.  Per panel: Li22 = inv(L22) (16 x 16, every CTA redundantly), N = Li22 L21,
-// Li21 = -N Li11; CTA c owns row l0 + c.  Runs after deim_block_update_kernel (needs its L21 rows).
-__global__ void __launch_bounds__(256)
-deim_block_linv_kernel(int k, int l0, int bw, const double* __restrict__ Lmb, const double* __restrict__ Lm,
-                       double* Li) {
-    __shared__ double li22[DEIM_BLOCK * DEIM_BLOCK], nrow[1024];
-    const int c = blockIdx.x, tid = threadIdx.x;
-    if (tid < bw) {   // column tid of inv(I + L22) by forward substitution
-        const int cc = tid;
-        for (int r = 0; r < bw; ++r) li22[r * DEIM_BLOCK + cc] = r == cc ? 1.0 : 0.0;
-        for (int r = cc + 1; r < bw; ++r) {
-            double a = 0.0;
-            for (int t = cc; t < r; ++t) a = fma(Lmb[r * bw + t], li22[t * DEIM_BLOCK + cc], a);
-            li22[r * DEIM_BLOCK + cc] = -a;
-        }
-    }
-    __syncthreads();
-    for (int x = tid; x < l0; x += 256) {
-        double a = 0.0;
-        for (int r = 0; r <= c; ++r) a = fma(li22[c * DEIM_BLOCK + r], Lm[(size_t)(l0 + r) * k + x], a);
-        nrow[x] = a;
-    }
-    __syncthreads();
-    for (int x = tid; x < l0; x += 256) {
-        double a = nrow[x];
-        for (int t = x + 1; t < l0; ++t) a = fma(nrow[t], __ldcg(&Li[(size_t)t * k + x]), a);
-        Li[(size_t)(l0 + c) * k + x] = -a;
-    }
-    if (tid < c) Li[(size_t)(l0 + c) * k + l0 + tid] = li22[c * DEIM_BLOCK + tid];
-}
-
-// Uf[t][l1 + q] = W12[t][q] + sum_{s < t} Li[t][s] * W12[s][q],  t < l1, q < bw     (Y12 = inv(L11) W12)
-__global__ void __launch_bounds__(256)
-deim_linv_apply_kernel(const double* __restrict__ Li, const double* __restrict__ W12, int k, int l1, int bw,
-                       double* __restrict__ Uf) {
-    const int t = blockIdx.x * DEIM_BLOCK + threadIdx.x / DEIM_BLOCK, q = threadIdx.x % DEIM_BLOCK;
-    if (t >= l1 || q >= bw) return;
-    double a0 = W12[t * DEIM_BLOCK + q], a1 = 0.0;
-    const double* li = Li + (size_t)t * k;
-    int sidx = 0;
-    for (; sidx + 2 <= t; sidx += 2) {
-        a0 = fma(li[sidx], W12[sidx * DEIM_BLOCK + q], a0);
-        a1 = fma(li[sidx + 1], W12[(sidx + 1) * DEIM_BLOCK + q], a1);
-    }
-    if (sidx < t) a0 = fma(li[sidx], W12[sidx * DEIM_BLOCK + q], a0);
-    Uf[(size_t)t * k + l1 + q] = a0 + a1;
-}
-
 // Coefficients of the next panel, packed for deim_panel_kernel: C = Z[0:l1, 0:l1] * Uf[0:l1, l1 : l1+bw]
 // (Uf[:, j] = inv(L) P'u_j is already part of the U-factor, Z = inv(Uf[0:l1, 0:l1])), i.e. column q of C
 // solves (P'U_l1) c = P'u_{l1+q}, deim.jl:21.  One CTA per 16-row slab: Cp[c][q][kk] = C[16 c + kk][q].
@@ -643,10 +522,6 @@ deim_block_coef_kernel(const double* __restrict__ Z, const double* __restrict__ 
 
 // MOR_B200_DEIM_BLOCK=0 selects the streaming path (one pass over columns 1..l per greedy step, the
 // reference's own access pattern); default is the blocked path whenever the basis layout allows it.
-static bool deim_blockupdate_enabled() {
-    const char* e = getenv("MOR_B200_DEIM_BLOCKUPDATE");
-    return e && e[0] == '1';
-}
 static bool deim_blocked_enabled() {
     const char* e = getenv("MOR_B200_DEIM_BLOCK");
     return !(e && e[0] == '0');
@@ -728,8 +603,7 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     double* W12 = Cp + (cp_doubles - (size_t)k * DEIM_BLOCK);   // deferred columns of the chosen rows (k x 16)
     // pipelined ingest: later columns of the basis are not there yet, so the k x k update is confined to the
     // columns of the current panel and the rest is caught up at each panel boundary
-    const bool blockupd = blocked && deim_blockupdate_enabled();
-    const bool defer = blocked && (col_ready != nullptr || blockupd);
+    const bool defer = blocked && col_ready != nullptr;
     if (!blocked && col_ready != nullptr)
         for (int g = 0; g * group_cols < (int)k; ++g) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[g], 0));
     // Blocked path: inside a block only the 16 x 16 factors of the panel decide the next coefficients, so the
@@ -767,18 +641,13 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         if (defer && col_ready != nullptr && i % group_cols == 0)
             MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[i / group_cols], 0));
         if (blocked && j == 0 && l0 > 0) {
-            if (!blockupd) {
-                MOR_CUDA(cudaEventRecord(ev_side, side));       // all earlier updates of the k x k factors
-                MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
-            }
+            MOR_CUDA(cudaEventRecord(ev_side, side));       // all earlier updates of the k x k factors
+            MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
             t_panel.start();
             if (defer) {
                 deim_gather_block_kernel<<<(l0 + 7) / 8, 128, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, W12);
                 if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W12, (size_t)l0 * DEIM_BLOCK));
-                if (blockupd)   // Wm is free in this mode (no per-step update of the k x k factors): it holds inv(L)
-                    deim_linv_apply_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(Wm, W12, (int)k, l0, bw, Uf);
-                else
-                    deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
+                deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
                 count_launch(2);
             }
             deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
@@ -811,11 +680,9 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0, defer ? l0 + bw : (int)k};
         ua.st[1] = ua.st[0];
         if (blocked) {
-            if (!blockupd) {
-                MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));   // record i is complete
-                MOR_CUDA(cudaStreamWaitEvent(side, ev_rec, 0));
-                deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
-            }
+            MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));   // record i is complete
+            MOR_CUDA(cudaStreamWaitEvent(side, ev_rec, 0));
+            deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
             UpdArgs ub;   // the panel's 16 x 16 factors and the sub-panel's 4 x 4 factors: two CTAs of one launch
             ub.st[0] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
                                 2 + (int)k, 1, bw};
@@ -823,13 +690,6 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
                                 2 + (int)k + DEIM_BLOCK, 1, sw};
             deim_update_kernel<<<2, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
             count_launch(4);
-            if (blockupd && j == bw - 1) {   // the panel is complete: extend the k x k factors in one step
-                deim_block_update_kernel<<<bw, 256, 0, cx.stream>>>(
-                    xfer.as<double>() + slot * (size_t)l0, slot, cx.nranks, rec, (int)k, l0, bw, bst + bb, bst + 2 * bb,
-                    bst + 3 * bb, Uf, Lm, Z, Zt, idx_d, l0 + bw >= (int)k ? 1 : 0, status_d);
-                deim_block_linv_kernel<<<bw, 256, 0, cx.stream>>>((int)k, l0, bw, bst + 2 * bb, Lm, Wm);
-                count_launch(2);
-            }
         } else {
             deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
             count_launch(3);

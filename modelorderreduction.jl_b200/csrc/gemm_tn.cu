@@ -286,13 +286,10 @@ int32_t gemm_tn(const double* A, int64_t lda, int p, const double* B, int64_t ld
     // share of the work, diagonal blocks computed as upper triangles (17 instead of 32 DMMAs per warp
     // and k-step), and the cut-off tails handed to the diagonal-block CTAs and to the SMs the plain
     // grid leaves idle.  Measured on B200, Gram of 16M x 1024: 515 ms vs 563 ms for launch_tn.
-    // MOR_B200_GEMM_TN_STREAMK selects the other schedules that were tried (all pass the parity tests):
-    // "classic" = launch_tn 563 ms; "0" tile-major stream-K 705 ms (loses the L2 sharing of the row
-    // groups, re-reads the matrix 9x from HBM in 160-byte pieces); "1" chunk-major 64 x 64 blocks 721 ms
-    // (small tiles: twice the operand traffic, 40 instead of 160 DMMAs per panel barrier); "2" the
-    // classic schedule through the segment kernel 570 ms (the machinery costs 1%).
+    // MOR_B200_GEMM_TN_STREAMK (A/B timing only): "classic" = launch_tn 563 ms; "2" = the classic schedule
+    // through the segment kernel 570 ms (the machinery costs 1%).
     static const char* sk = getenv("MOR_B200_GEMM_TN_STREAMK");
-    if (!sk || strcmp(sk, "classic") != 0) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, sk ? atoi(sk) : 3);
+    if (!sk || strcmp(sk, "classic") != 0) return gemm_tn_streamk(A, lda, p, B, ldb, q, m, C, ldc, accumulate, (sk && sk[0] == '2') ? 2 : 3);
     return launch_tn<128, 128, 32, 64, 20, 5, 1>(A, lda, p, B, ldb, q, m, C, ldc, accumulate);
 }
 

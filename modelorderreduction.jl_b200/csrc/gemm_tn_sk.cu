@@ -15,8 +15,9 @@
 //           triangles only (run_segment_tri: 17 instead of 32 DMMAs per warp and k-step, perfectly
 //           balanced over the 8 warps), and the cut-off tails of the off-diagonal tiles (13% of the
 //           rows) go to the diagonal-block CTAs and to the otherwise idle SMs.  515 ms vs 563 ms.
-//   mode 0  tile-major stream-K, mode 1 chunk-major 64 x 64 blocks, mode 2 classic schedule through
-//           this kernel: measured slower (705 / 721 / 570 ms), kept for reference.
+//   mode 2  the classic schedule run through this kernel (no cap; A/B timing of the machinery: 570 ms).
+//   Tile-major stream-K (705 ms) and chunk-major 64 x 64 blocks (721 ms) were measured in round 1 and removed;
+//   DESIGN.md section 4 keeps the numbers.
 #include <cuda.h>
 
 #include <cstdio>
@@ -269,12 +270,7 @@ gemm_tn_sk_reduce_kernel(const double* __restrict__ part, const TileInfo* __rest
 
 }  // namespace
 
-// C (p x q) = A' * B, or the symmetric Gram matrix when A == B.  Requires p, q > 64.
-// mode 0: tile-major stream-K (128 x 128 tiles + split diagonal blocks, contiguous equal-cost pieces);
-// mode 1: chunk-major 64 x 64 blocks -- the rows are cut into NCH chunks, the work items (chunk, block)
-//         are dealt round-robin to the CTAs in chunk-major order, so all CTAs sweep the rows together
-//         (a panel is fetched from HBM about twice instead of 9x) and every SM gets the same number of
-//         equal-cost items to within one.
+// C (p x q) = A' * B, or the symmetric Gram matrix when A == B.  Requires p, q > 64.  mode: 3 (default) or 2.
 int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t m, double* C,
                         int ldc, int accumulate, int mode) {
     Ctx& cx = ctx();
@@ -285,31 +281,7 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
     std::vector<int> cta_seg(1, 0);
     long long part_doubles = 0;
     int nct = cx.num_sms;
-    if (mode == 1) {
-        const int bp = (p + 63) / 64, bq = (q + 63) / 64;
-        for (int bi = 0; bi < bp; ++bi)
-            for (int bj = same ? bi : 0; bj < bq; ++bj) tiles.push_back({bi * 64, bj * 64, 1, (same && bi == bj) ? 1 : 0, 0, 0});
-        const long long ntiles = (long long)tiles.size();
-        long long nch = (30LL * nct + ntiles - 1) / ntiles;      // ~30 items per CTA
-        nch = std::max<long long>(1, std::min(nch, P / 64));     // but at least 64 panels per item
-        for (long long t = 0; t < ntiles; ++t) {
-            tiles[t].part_base = t * nch * 4096;
-            tiles[t].nparts = (int)nch;
-        }
-        part_doubles = ntiles * nch * 4096;
-        const long long nitems = ntiles * nch;
-        if (nitems < nct) nct = (int)nitems;
-        cta_seg.clear();
-        for (int c = 0; c < nct; ++c) {
-            cta_seg.push_back((int)segs.size());
-            for (long long id = c; id < nitems; id += nct) {
-                const long long ch = id / ntiles, t = id % ntiles;
-                segs.push_back({tiles[t].a_col, tiles[t].b_col, 1, tiles[t].diag, P * ch / nch, P * (ch + 1) / nch,
-                                tiles[t].part_base + ch * 4096});
-            }
-        }
-        cta_seg.push_back((int)segs.size());
-    } else if (mode == 2 || mode == 3) {
+    {
         // Lock-step first, balance second.  Primary assignment = the classic one: G row groups x one CTA
         // per (128 x 128 tile | diagonal block), every CTA starting at the first panel of its group so the
         // group sweeps its rows together and shares them through L2.  mode 3 then caps every CTA at the
@@ -414,50 +386,6 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
             }
         }
         cta_seg.push_back((int)segs.size());
-    } else {
-    // ---- tiles -------------------------------------------------------------------------------
-    const int tp = (p + 127) / 128, tq_ = (q + 127) / 128;
-    for (int ti = 0; ti < tp; ++ti)
-        for (int tj = same ? ti : 0; tj < tq_; ++tj) {
-            if (same && ti == tj) {
-                const int c0 = ti * 128;
-                tiles.push_back({c0, c0, 1, 1, 0, 0});
-                if (c0 + 64 < p) {
-                    tiles.push_back({c0, c0 + 64, 1, 0, 0, 0});
-                    tiles.push_back({c0 + 64, c0 + 64, 1, 1, 0, 0});
-                }
-            } else {
-                tiles.push_back({ti * 128, tj * 128, 0, 0, 0, 0});
-            }
-        }
-    // ---- equal-cost contiguous pieces, one per SM ----------------------------------------------
-    long long total = 0;
-    for (const TileInfo& t : tiles) total += (t.small ? 1 : 4) * P;
-    if (total < (long long)nct * 16) nct = (int)std::max<long long>(1, total / 16);  // tiny problems: fewer CTAs
-    int cta = 0;
-    long long quota = (total + nct - 1) / nct, left = quota;
-    for (TileInfo& t : tiles) {
-        const int cost = t.small ? 1 : 4;
-        t.part_base = part_doubles;
-        t.nparts = 0;
-        long long pb = 0;
-        while (pb < P) {
-            const bool last = (cta + 1 >= nct);
-            if (!last && left < cost) {  // this CTA's share is used up: open the next one
-                cta_seg.push_back((int)segs.size());
-                ++cta;
-                left = quota;
-                continue;
-            }
-            const long long take = last ? (P - pb) : std::min(P - pb, left / cost);
-            segs.push_back({t.a_col, t.b_col, t.small, t.diag, pb, pb + take, part_doubles});
-            part_doubles += t.small ? 64 * 64 : 128 * 128;
-            ++t.nparts;
-            pb += take;
-            left -= take * cost;
-        }
-    }
-    while ((int)cta_seg.size() < nct + 1) cta_seg.push_back((int)segs.size());
     }
     segs.push_back({0, 0, 0, 0, 0, 0, 0});  // sentinel for the producer cursor
 

@@ -83,6 +83,8 @@ SIGNATURES = {
 }
 
 _lib = None
+_test_lib = None
+TEST_LIB = _PKG_ROOT / "lib" / "libmor_b200_test.so"
 
 
 def lib_path() -> Path:
@@ -106,6 +108,18 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def load_test() -> C.CDLL:
+    """libmor_b200_test.so: kernel-level test hooks and peak probes (mor_dbg_*).  Not part of the product
+    ABI; used by tests/ and bench.py only."""
+    global _test_lib
+    if _test_lib is None:
+        load()
+        if not TEST_LIB.exists():
+            raise FileNotFoundError(f"{TEST_LIB} not found: build it with make -C modelorderreduction.jl_b200/csrc")
+        _test_lib = C.CDLL(str(TEST_LIB), mode=C.RTLD_GLOBAL)
+    return _test_lib
 
 
 def check(status: int) -> None:
