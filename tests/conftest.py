@@ -21,6 +21,23 @@ def golden():
         return json.load(f)
 
 
+def _unhex(rows):
+    import struct
+    return np.asfortranarray([[struct.unpack(">d", bytes.fromhex(v))[0] for v in row] for row in rows])
+
+
+@pytest.fixture(scope="session")
+def mp_golden():
+    """50-digit mpmath answers (oracle/make_golden_mpmath.py): the pin that is independent of LAPACK."""
+    with open(os.path.join(ROOT, "tests", "golden", "mpmath_golden.json")) as f:
+        g = json.load(f)
+    g["F2"]["U"] = _unhex(g["F2"]["U_hex"])
+    g["F2"]["Q5"] = _unhex(g["F2"]["Q5_hex"])
+    for c in g["deim_random"]:
+        c["basis"] = _unhex(c["basis_hex"])
+    return g
+
+
 @pytest.fixture(scope="session")
 def gpu():
     """Initialises libmor_b200 on cuda:0.  A missing library is an error (never a skip);

@@ -228,3 +228,49 @@ def test_blocked_path_exact_ties_across_blocks(gpu, monkeypatch):
     idx = mor_b200.deim_interpolation_indices(np.asfortranarray(A))
     assert idx.tolist() == O.deim_interpolation_indices(A).tolist()
     assert not np.any((idx > 20_000))             # the duplicate with the higher index never wins
+
+
+def test_mpmath_goldens(gpu, mp_golden):
+    """The independent pin: indices from the 50-digit evaluation of deim.jl:13-24 (oracle/make_golden_mpmath.py),
+    every step decided by a margin > 1e-3."""
+    f2 = mp_golden["F2"]
+    for basis, chain in ((f2["U"], f2["deim_U10"]), (f2["Q5"], f2["deim_Q5"])) + \
+            tuple((c["basis"], c["chain"]) for c in mp_golden["deim_random"]):
+        assert mor_b200.deim_interpolation_indices(np.asfortranarray(basis)).tolist() == chain["indices"]
+
+
+def _first_difference_report(got, want, margins):
+    t = int(np.flatnonzero(np.asarray(got) != np.asarray(want))[0])
+    return f"first difference at step {t + 1}: got row {got[t]}, oracle row {want[t]}, oracle margin {margins[t]:.3e}"
+
+
+@pytest.mark.parametrize("kind", ["gauss", "burgers"])
+def test_headline_k256_vs_oracle(gpu, monkeypatch, kind):
+    """k = 256, the headline DEIM dimension (BASELINE config 5), at the largest size the oracle finishes in
+    seconds (262,144 rows): the blocked path, the streaming path and the host-pointer entry (pipelined column
+    groups, deferred columns) against deim.jl:9-28 restated, Int64 equality."""
+    from mor_b200.device import orthonormalize_dev, pod_factor_dev
+    m, k = 262_144, 256
+    monkeypatch.delenv("MOR_B200_DEIM_BLOCK", raising=False)
+    if kind == "gauss":
+        B = DeviceMatrix.alloc(m, k).synth(_lib.SYNTH_GAUSS, seed=5, param=1.0 / np.sqrt(m))
+        orthonormalize_dev(B)
+    else:        # POD basis (this library, SVD(), all 256 modes) of Burgers snapshots on a 512 x 512 grid
+        S = DeviceMatrix.alloc(m, k).synth(_lib.SYNTH_BURGERS, seed=5, param=2e-3, iparam=512)
+        f = pod_factor_dev(S, _lib.MOR_SVD, k, flags=_lib.POD_MAY_OVERWRITE)
+        B = f.basis(k, DeviceMatrix.alloc(m, k))
+        f.free(); S.free()
+    Bh = B.to_host()
+    assert np.abs(Bh.T @ Bh - np.eye(k)).max() < 1e-10
+    want, margins = O.deim_interpolation_indices(Bh, return_margins=True)
+    want = want.tolist()
+    got = deim_indices_dev(B).tolist()
+    assert _lib.last_timings()["deim_blocked"] == 1.0
+    assert got == want, "blocked: " + _first_difference_report(got, want, margins)
+    got = mor_b200.deim_interpolation_indices(Bh).tolist()          # host pointers: pipelined ingest
+    assert got == want, "host entry: " + _first_difference_report(got, want, margins)
+    monkeypatch.setenv("MOR_B200_DEIM_BLOCK", "0")
+    got = deim_indices_dev(B).tolist()
+    assert _lib.last_timings()["deim_blocked"] == 0.0
+    assert got == want, "streaming: " + _first_difference_report(got, want, margins)
+    assert len(set(want)) == k

@@ -44,6 +44,38 @@ def test_f2_sin_fixture_golden(golden):
     assert O.deim_interpolation_indices(U).tolist() == golden["F2"]["deim_U10"]
 
 
+def test_oracle_pinned_by_mpmath_goldens(mp_golden, golden):
+    """The independent pin (missing #1): the oracle's LAPACK answers on the reference's own fixture
+    (src/precompile.jl:5-12) against 50-digit mpmath values computed without LAPACK/BLAS, and the DEIM chain of
+    deim.jl:13-24 against its 50-digit evaluation -- with the margin by which each argmax is decided."""
+    f2 = mp_golden["F2"]
+    S = sin_fixture()
+    _, s, _ = O._svd(S)
+    s_mp = np.array(f2["sigma"])
+    # kappa = 2e10: dgesdd is accurate to ~eps * sigma_1 in absolute terms, so the gate is SURVEY 8d's
+    # (relative above 1e-5 sigma_1, absolute / sigma_1 below)
+    assert O.sigma_error(s_mp, s) <= 1e-10
+    assert np.max(np.abs(s - s_mp)) <= 8 * np.finfo(float).eps * s_mp[0]
+    assert O.sigma_error(s_mp, np.array(golden["F2"]["spectrum"])) <= 1e-10      # the committed LAPACK golden too
+    pod = O.POD(S, 3); O.reduce(pod, O.SVD())
+    assert pod.renergy == pytest.approx(f2["renergy_svd_k3"], rel=1e-13)
+    pod = O.POD(S, 3); O.reduce(pod, O.TSVD())
+    assert pod.renergy == pytest.approx(f2["renergy_tsvd_k3"], rel=1e-13)
+    u, _, _ = O._svd(S)
+    # left vectors: sigma_1 - sigma_2 = 1.1e-3, so columns 1, 2 are only determined to ~eps / gap
+    assert O.subspace_sine(f2["U"][:, :4], u[:, :4]) <= 1e-12
+    for basis, chain in ((f2["U"], f2["deim_U10"]), (f2["Q5"], f2["deim_Q5"])) + \
+            tuple((c["basis"], c["chain"]) for c in mp_golden["deim_random"]):
+        assert chain["min_relative_margin"] > 1e-3           # decided far above any FP64 rounding error
+        assert O.deim_interpolation_indices(basis).tolist() == chain["indices"]
+        assert O.deim_interpolation_indices_blocked(basis, block=4, sub=2).tolist() == chain["indices"]
+    # the LAPACK-made bases of golden.json select the same points as the mpmath-made ones
+    assert golden["F2"]["deim_U10"] == f2["deim_U10"]["indices"]
+    assert golden["F2"]["deim_Q5"] == f2["deim_Q5"]["indices"]
+    Q, _ = sla.qr(S, mode="economic")
+    assert np.max(np.abs(np.abs(Q[:, :5]) - np.abs(f2["Q5"]))) <= 1e-14
+
+
 def test_f5_truncation_quirks(golden):
     s = np.array([4.0, 3.0, 2.0, 1.0])
     # probe from SURVEY 8a: mre=0.5 -> (2, 0.6) although the true 2-mode energy is 0.7

@@ -284,3 +284,37 @@ def test_abi_error_paths(gpu):
     idx = np.zeros(1025, dtype=np.int64)
     B = np.zeros((2000, 1025), order="F")
     assert lib.mor_b200_deim_indices(B.ctypes.data, 2000, 1025, 2000, idx.ctypes.data) == _lib.ERR_ARG
+
+
+def test_mpmath_goldens(gpu, mp_golden):
+    """The independent pin: singular values / energies / leading subspace of the reference's sin(i*j/n) fixture
+    (src/precompile.jl:5-12) against 50-digit mpmath values (oracle/make_golden_mpmath.py)."""
+    f2 = mp_golden["F2"]
+    S = sin_fixture()
+    pod = mor_b200.POD(S, 3)
+    mor_b200.reduce(pod, mor_b200.SVD())
+    assert O.sigma_error(np.array(f2["sigma"]), pod.spectrum) <= SIGMA_TOL
+    assert pod.renergy == pytest.approx(f2["renergy_svd_k3"], rel=1e-10)
+    assert O.subspace_sine(f2["U"][:, :3], pod.rbasis) <= ANGLE_TOL
+    pod = mor_b200.POD(S, 3)
+    mor_b200.reduce(pod, mor_b200.TSVD())
+    assert pod.renergy == pytest.approx(f2["renergy_tsvd_k3"], rel=1e-10)
+    np.testing.assert_allclose(pod.spectrum, f2["sigma"][:3], rtol=1e-12)
+
+
+def test_config2_exact_through_host_abi(gpu):
+    """BASELINE config 2 exactly: synthetic 1,048,576 x 256 FP64 snapshot matrix (N(0,1) * 10^(-3j/(n-1)), Philox
+    seed 2), reduce!(POD(X, 32), SVD()) through the host-pointer ABI (what the Julia shim calls), against dgesdd on
+    the same matrix: all 256 singular values, the 32 modes, the energy."""
+    m, n, k = 1_048_576, 256, 32
+    Xh = DeviceMatrix.alloc(m, n).synth(_lib.SYNTH_GRADED, seed=2, param=3.0).to_host()
+    pod = mor_b200.POD(Xh, k)
+    assert mor_b200.reduce(pod, mor_b200.SVD()) is None
+    u_ref, s_ref, _ = O._svd(Xh)
+    assert pod.spectrum.shape == (n,) and pod.rbasis.shape == (m, k) and pod.nmodes == k
+    assert O.sigma_error(s_ref, pod.spectrum) <= SIGMA_TOL
+    assert O.subspace_sine(u_ref[:, :k], pod.rbasis) <= ANGLE_TOL
+    ref = O.POD(Xh, k)
+    ref.nmodes, ref.renergy = O.determine_truncation(s_ref, k, k, 0.0)
+    assert pod.renergy == pytest.approx(ref.renergy, rel=1e-10)
+    assert np.abs(pod.rbasis.T @ pod.rbasis - np.eye(k)).max() <= 1e-11
