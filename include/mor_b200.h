@@ -122,6 +122,15 @@ int32_t mor_b200_pod_info(mor_pod_t handle, int32_t* passes, int32_t* sweeps);
  * 1-based row indices (identical on every rank).  First-maximal-index tie-break, NaN
  * counts as maximal (Julia argmax). */
 int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out);
+/* How firmly the last DEIM call on this rank decided each greedy step: values[l] = r_best, the winning residual of
+ * deim.jl:23 at step l+1, margins[l] = (r_best - r_second) / r_best (0 = exact tie).  Writes min(count, cap) entries;
+ * *min_margin / *min_step (1-based) are taken over steps >= 2 (step 1 is the argmax of |u_1| itself: no arithmetic,
+ * identical in every formulation).  The default blocked path rounds differently from deim.jl:21-23; when a step >= 2
+ * is decided by less than 32 k eps (MOR_B200_DEIM_TIE_TOL overrides) the library repeats the call with the streaming
+ * path, the reference's own formulation (MOR_B200_DEIM_TIE_FALLBACK=0 disables; MOR_T_DEIM_FALLBACK tells).
+ * Any pointer may be NULL. */
+int32_t mor_b200_deim_last_margins(double* margins, double* values, int64_t cap, int64_t* count, double* min_margin,
+                                   int64_t* min_step);
 
 /* DEIM projector, deim.jl:150: P = ((U[idx, :])' \ (U' * V))'  (pod_dim x deim_dim, ld = ldp),
  * U (m x kd) the DEIM basis, V (m x kp) the POD basis (this rank's row shards), idx the kd global
@@ -180,12 +189,16 @@ int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx
 #define MOR_T_CORE 4      /* n x n work: Cholesky, inverse, Jacobi SVD             */
 #define MOR_T_BASIS 5     /* U_k = X*W                                             */
 #define MOR_T_COMM 6      /* NCCL collectives                                      */
-#define MOR_T_DEIM_STEP 7 /* sum of the fused residual+argmax kernels              */
-#define MOR_T_DEIM_TAIL 8 /* sum of the per-step small kernels                     */
+#define MOR_T_DEIM_STEP 7 /* the fused residual+argmax(+tail) kernels: total - panel - update */
+#define MOR_T_DEIM_TAIL 8 /* part of DEIM_STEP spent in the per-step tails (reduction, exchange, small LU updates) */
 #define MOR_T_D2H 9
 #define MOR_T_SKETCH 10   /* RSVD: Y = X*Omega and B = Q'X                        */
 #define MOR_T_DEIM_PANEL 11 /* DEIM blocked path: panel residual kernels (one per 16 columns) */
 #define MOR_T_DEIM_BLOCKED 12 /* not a time: 1 if the last DEIM call took the blocked path, else 0 */
+#define MOR_T_DEIM_UPDATE 13 /* DEIM blocked path: per-panel coefficient and inverse-update kernels */
+#define MOR_T_DEIM_FALLBACK 14 /* not a time: 1 if a near-tie made the last DEIM call repeat on the streaming path */
+#define MOR_T_DEIM_EXCHANGE 15 /* not a time: per-step candidate exchange of the last DEIM call: 0 single rank,
+                                  1 peer mailboxes over NVLink (stores + flags inside the step kernel), 2 ncclAllGather */
 #define MOR_T_NSLOTS 16
 int32_t mor_b200_last_timings(double* ms, int32_t n);
 /* number of kernel launches issued by the library since the last reset (this rank) */

@@ -258,6 +258,7 @@ int32_t mor_b200_shutdown(void) {
         if (g_ctx.ingest_p) cudaFree(g_ctx.ingest_p);
         g_ctx.ingest_p = nullptr;
         g_ctx.ingest_bytes = 0;
+        deim_mailbox_release();
         if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
         g_ctx.copy_stream = nullptr;
         if (g_ctx.aux_stream) cudaStreamDestroy(g_ctx.aux_stream);

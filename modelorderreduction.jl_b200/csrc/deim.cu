@@ -1,20 +1,22 @@
 // DEIM interpolation-index selection -- replaces the body of deim_interpolation_indices,
 // /root/reference/src/deim.jl:9-28.
 //
-// Per greedy step l (reference lines in brackets):
-//   deim_step_kernel    r_i = |u_l[i] - sum_j U[i,j] c_j| fused with the abs-argmax   [l.22-24]
-//                       -- one streaming pass over columns 1..l of the basis, HBM-bound.
-//   deim_local_kernel   reduce the per-CTA candidates, gather the winner's basis row [l.16-20]
-//   (ncclAllGather)     (value, global index, row) of every rank                  (multi-GPU)
-//   deim_update_kernel  pick the global winner (value, then LOWEST global index = Julia's
-//                       first-index tie-break, NaN maximal), append its row to P'U and
-//                       solve (P'U) c = P'u_{l+1} for the next step                    [l.21]
+// Per greedy step l (reference lines in brackets) ONE kernel launch does everything:
+//   streaming body   r_i = |u_l[i] - sum_j U[i,j] c_j| fused with the abs-argmax and the runner-up     [l.22-24]
+//                    (deim_step_kernel; deim_step4_kernel forms the next 4 residual columns of a panel)
+//   fused tail       executed by the LAST CTA of the grid to finish (atomic ticket):
+//                      reduce the per-CTA candidates, gather the winner's rows                        [l.16-20]
+//                      exchange the record with the other ranks: plain stores into every peer's mailbox over
+//                      NVLink + a flag per (slot, rank), then poll the own flags (no NCCL call on the chain)
+//                      pick the global winner (value, then LOWEST global index = Julia's first-index
+//                      tie-break, NaN maximal), record the margin to the runner-up
+//                      extend the LU factors of the panel's 16 x 16 and the sub-panel's 4 x 4 pivot blocks by
+//                      one row (bordered update) and solve for the next step's coefficients            [l.21]
+// The k x k system of deim.jl:21 is only needed once per 16-column panel: A = inv(P'U) is kept explicitly and
+// extended per panel by the block-inverse formula with the panel's own factors (three small launches).
 //
-// The small solve keeps the LU factors of P'U incrementally: P'U grows by one row and one
-// column per step and the greedy choice IS partial pivoting (the pivot is the residual of
-// largest magnitude), so the bordered Doolittle update reproduces dgetrf's factorisation
-// without row exchanges.  Z = inv(U-factor) is kept explicitly so every phase is a parallel
-// dot product instead of a 255-long dependent substitution chain.
+// The streaming path (MOR_B200_DEIM_BLOCK=0, k <= 16, or a basis the bulk copies cannot take) is the reference's
+// own access pattern: one pass over columns 1..l per step, coefficients from the bordered LU of the k x k block.
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
@@ -27,6 +29,7 @@ namespace mor {
 struct Cand {
     double val;
     long long idx;
+    double val2;   // largest value at any OTHER row seen by this candidate's owner (runner-up)
 };
 
 #define MOR_IDX_NONE LLONG_MAX
@@ -40,32 +43,57 @@ __device__ __forceinline__ bool cand_better(double va, long long ia, double vb, 
     return (va > vb) || (va == vb && ia < ib);
 }
 
-__device__ __forceinline__ void cand_warp_reduce(double& v, long long& i) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, off);
-        long long oi = __shfl_xor_sync(0xffffffffu, i, off);
-        if (cand_better(ov, oi, v, i)) {
-            v = ov;
-            i = oi;
-        }
+// merge candidate (ov, oi, os) into (v, i, s): the loser's best value competes for the runner-up slot
+__device__ __forceinline__ void cand_merge(double& v, long long& i, double& s, double ov, long long oi, double os) {
+    s = fmax(s, os);
+    if (cand_better(ov, oi, v, i)) {
+        if (i != MOR_IDX_NONE) s = fmax(s, v);
+        v = ov;
+        i = oi;
+    } else if (oi != MOR_IDX_NONE) {
+        s = fmax(s, ov);
     }
 }
 
+__device__ __forceinline__ void cand_warp_reduce(double& v, long long& i, double& s) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, i, off);
+        const double os = __shfl_xor_sync(0xffffffffu, s, off);
+        cand_merge(v, i, s, ov, oi, os);
+    }
+}
+
+constexpr int DEIM_THREADS = 256;
+constexpr int DEIM_WARPS = DEIM_THREADS / 32;
+constexpr int DEIM_BLOCK = 16;   // panel width of the blocked path (= the 16-column stages of deim_panel_kernel)
+constexpr int DEIM_SUB = 4;      // sub-panel width inside a panel (deim_step4_kernel)
+constexpr int DEIM_MAXK = 1024;
+constexpr int DEIM_MAXRANKS = MBOX_MAXRANKS;
+constexpr int DEIM_SLOTS = MBOX_SLOTS;    // mailbox ring: a rank is never more than one step ahead of its peers
+constexpr int DEIM_REC_MAX = MBOX_REC_MAX;
+// small (panel / sub-panel) LU state: Uf | L | Z (dim x dim, row-major with fixed stride) | c (dim)
+constexpr int BST_DOUBLES = 3 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK;
+constexpr int SST_DOUBLES = 3 * DEIM_SUB * DEIM_SUB + DEIM_SUB;
+constexpr int SBUF_DOUBLES = DEIM_REC_MAX + 5;   // >= record, >= BST + SST + 20
+
 // block-wide reduce; result valid in thread 0
-template <int NWARPS>
-__device__ __forceinline__ void cand_block_reduce(double& v, long long& i, double* sv, long long* si) {
-    cand_warp_reduce(v, i);
+__device__ __forceinline__ void cand_block_reduce(double& v, long long& i, double& s, double* sv, long long* si,
+                                                  double* ss) {
+    cand_warp_reduce(v, i, s);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         sv[warp] = v;
         si[warp] = i;
+        ss[warp] = s;
     }
     __syncthreads();
     if (warp == 0) {
-        v = lane < NWARPS ? sv[lane] : -1.0;
-        i = lane < NWARPS ? si[lane] : MOR_IDX_NONE;
-        cand_warp_reduce(v, i);
+        v = lane < DEIM_WARPS ? sv[lane] : -1.0;
+        i = lane < DEIM_WARPS ? si[lane] : MOR_IDX_NONE;
+        s = lane < DEIM_WARPS ? ss[lane] : -1.0;
+        cand_warp_reduce(v, i, s);
     }
 }
 
@@ -80,28 +108,265 @@ __device__ __forceinline__ double ld_stream1(const double* p) {
     return v;
 }
 
-// running best of one thread; rows arrive in ascending order so ties keep the earlier row
-__device__ __forceinline__ void cand_take(double& bv, long long& bi, double v, long long idx) {
-    if (!(bv != bv) && ((v != v) || v > bv)) {
-        bv = v;
-        bi = idx;
+// running best / runner-up of one thread; rows arrive in ascending order so ties keep the earlier row
+__device__ __forceinline__ void cand_take(double& bv, long long& bi, double& b2, double v, long long idx) {
+    if (!(bv != bv)) {
+        if ((v != v) || v > bv) {
+            b2 = bv;
+            bv = v;
+            bi = idx;
+        } else if (v > b2) {
+            b2 = v;
+        }
     }
 }
 
-constexpr int DEIM_THREADS = 256;
-constexpr int DEIM_BLOCK = 16;   // panel width of the blocked path (= the 16-column stages of deim_panel_kernel)
-constexpr int DEIM_SUB = 4;      // sub-panel width inside a panel (deim_step4_kernel)
+// ---- system-scope flag traffic of the peer exchange ------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
-// Fused residual + abs-argmax over this rank's rows.  l = number of previous columns.
+// Everything the fused tail needs (passed by value to the step kernels).
+struct TailArgs {
+    unsigned* ticket;                 // last-CTA election
+    Cand* cands;                      // one candidate per CTA of this launch
+    // rows gathered at the local winner
+    const double* U;                  // basis shard
+    int64_t ldU;
+    int k, kcols;                     // record carries U[idx, 0..kcols), zeros beyond (columns still on the PCIe link)
+    const double* Pn;                 // residual panel (blocked path) or nullptr
+    int64_t ldn;
+    int bw;
+    const double* P2;                 // sub-panel or nullptr
+    int64_t ld2;
+    int sw;
+    int64_t row_offset;
+    // exchange
+    double* box;                      // own mailbox: DEIM_SLOTS x nranks records
+    unsigned long long* flags;        // own flags: DEIM_SLOTS x DEIM_MAXRANKS
+    double* peer_box[DEIM_MAXRANKS];  // peers' mailboxes (NVLink peer memory); [rank] = own
+    unsigned long long* peer_flags[DEIM_MAXRANKS];
+    double* send;                     // NCCL fallback: the local record goes here instead
+    int rank, nranks, rec, slot;
+    unsigned long long expect;        // flag value of this step
+    int mode;                         // 0: fused (local + peer exchange + global), 1: local part only (NCCL follows)
+    // global part
+    double* W;                        // k x k rows of the basis at the chosen points (row-major, stride k)
+    long long* idx_out;
+    double* margins;
+    double* values;                   // winning residual of every step
+    int i;                            // greedy step
+    int blocked;
+    double *bst, *sst, *Dsub;         // panel / sub-panel LU state, next sub-panel's coefficients
+    int j, jj, s0;                    // step inside the panel / sub-panel, first panel column of the sub-panel
+    int last;                         // final greedy step of the call (a zero pivot no longer matters)
+    int* status;
+    unsigned long long* tail_ns;      // accumulated duration of the tails (globaltimer)
+};
+
+// One bordered (Doolittle) update of a small LU state by ONE warp: append row i (values w[0..dim)), then solve for
+// the coefficients of column i + 1.  The greedy choice is partial pivoting, so no row exchanges are needed and the
+// factorisation equals dgetrf's.  Z = inv(Uf) is kept explicitly: every phase is a set of independent dot products.
+template <int S>
+__device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, double* Z, double* c, int i, int dim,
+                                                     const double* w) {
+    const int x = threadIdx.x & 31;
+    if (x < i) {   // L row i:  ell[x] = sum_{t <= x} w[t] Z[t][x]
+        double s = 0.0;
+        for (int t = 0; t <= x; ++t) s = fma(w[t], Z[t * S + x], s);
+        L[i * S + x] = s;
+    }
+    __syncwarp();
+    if (x >= i && x < dim) {   // U-factor row i:  Uf[i][x] = w[x] - sum_{t < i} ell[t] Uf[t][x]
+        double s = 0.0;
+        for (int t = 0; t < i; ++t) s = fma(L[i * S + t], Uf[t * S + x], s);
+        Uf[i * S + x] = w[x] - s;
+    }
+    __syncwarp();
+    const double pivot = Uf[i * S + i];
+    if (x < i) {   // Z column i:  Z[x][i] = -(sum_{t = x}^{i-1} Z[x][t] Uf[t][i]) / pivot
+        double s = 0.0;
+        for (int t = x; t < i; ++t) s = fma(Z[x * S + t], Uf[t * S + i], s);
+        Z[x * S + i] = -s / pivot;
+    } else if (x == i) {
+        Z[i * S + i] = 1.0 / pivot;
+    }
+    __syncwarp();
+    if (i + 1 < dim && x <= i) {   // c = Z[0:i+1, 0:i+1] * Uf[0:i+1, i+1]
+        double s = 0.0;
+        for (int t = x; t <= i; ++t) s = fma(Z[x * S + t], Uf[t * S + i + 1], s);
+        c[x] = s;
+    }
+    __syncwarp();
+}
+
+// Global part of the tail: `gathered` holds one record per rank.  Runs in one CTA of DEIM_THREADS threads.
+__device__ void deim_tail_global(const TailArgs& a, const double* gathered, double* sbuf) {
+    __shared__ int win_s;
+    __shared__ double wrow[DEIM_BLOCK], w2row[DEIM_SUB];
+    const int tid = threadIdx.x, k = a.k, rec = a.rec;
+    if (tid == 0) {
+        int win = 0;
+        double bv = -1.0, b2 = -1.0;
+        long long bi = MOR_IDX_NONE;
+        for (int r = 0; r < a.nranks; ++r) {
+            const double v = __ldcg(&gathered[(size_t)r * rec]);
+            const long long ix = __double_as_longlong(__ldcg(&gathered[(size_t)r * rec + 1]));
+            const double s = __ldcg(&gathered[(size_t)r * rec + rec - 1]);
+            const long long before = bi;
+            cand_merge(bv, bi, b2, v, ix, s);
+            if (bi != before) win = r;
+        }
+        win_s = win;
+        a.idx_out[a.i] = bi + 1;   // 1-based, like Julia
+        a.values[a.i] = bv;
+        // relative gap to the runner-up: by how much this argmax is decided (0: exact tie / NaN / zero residual)
+        a.margins[a.i] = (bv == bv && bv > 0.0 && b2 >= 0.0) ? (bv - b2) / bv : (bv > 0.0 && b2 < 0.0 ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const double* src = gathered + (size_t)win_s * rec;
+    for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = __ldcg(&src[2 + jx]);
+    if (!a.blocked) return;
+    if (tid < DEIM_BLOCK) wrow[tid] = __ldcg(&src[2 + k + tid]);
+    if (tid >= 32 && tid < 32 + DEIM_SUB) w2row[tid - 32] = __ldcg(&src[2 + k + DEIM_BLOCK + tid - 32]);
+    // the small LU states live in global memory between the steps; work on them in shared memory
+    double* bs = sbuf;
+    double* ss = sbuf + BST_DOUBLES;
+    for (int e = tid; e < BST_DOUBLES; e += DEIM_THREADS) bs[e] = __ldcg(&a.bst[e]);
+    if (tid < SST_DOUBLES) ss[tid] = __ldcg(&a.sst[tid]);
+    __syncthreads();
+    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK, SS = DEIM_SUB * DEIM_SUB;
+    const int warp = tid >> 5;
+    if (warp == 0) bordered_update_warp<DEIM_BLOCK>(bs, bs + BB, bs + 2 * BB, bs + 3 * BB, a.j, a.bw, wrow);
+    if (warp == 1) bordered_update_warp<DEIM_SUB>(ss, ss + SS, ss + 2 * SS, ss + 3 * SS, a.jj, a.sw, w2row);
+    __syncthreads();
+    // the pivot is the residual at the chosen row: exactly zero <=> P'U singular (SingularException in the reference)
+    if (tid == 0 && bs[a.j * DEIM_BLOCK + a.j] == 0.0 && !a.last && *a.status == 0) *a.status = a.i + 1;
+    for (int e = tid; e < BST_DOUBLES; e += DEIM_THREADS) a.bst[e] = bs[e];
+    if (tid < SST_DOUBLES) a.sst[tid] = ss[tid];
+    // the next step opens a new sub-panel of this panel: its coefficients with respect to the s0n points chosen so
+    // far in the panel, D (16 x 4 column-major, zero padded) = Zb[0:s0n, 0:s0n] * Ufb[0:s0n, s0n : s0n+swn]
+    const int s0n = a.s0 + a.sw;
+    if (a.jj + 1 == a.sw && s0n < a.bw && tid < DEIM_BLOCK * DEIM_SUB) {
+        const int t = tid % DEIM_BLOCK, q = tid / DEIM_BLOCK;
+        const int swn = a.bw - s0n < DEIM_SUB ? a.bw - s0n : DEIM_SUB;
+        double s = 0.0;
+        if (t < s0n && q < swn)
+            for (int r = t; r < s0n; ++r) s = fma(bs[2 * BB + t * DEIM_BLOCK + r], bs[r * DEIM_BLOCK + s0n + q], s);
+        a.Dsub[q * DEIM_BLOCK + t] = s;
+    }
+}
+
+// The tail, entered by every thread of the LAST CTA of a step kernel.
+__device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2) {
+    __shared__ long long widx_s;
+    const int tid = threadIdx.x, k = a.k, rec = a.rec;
+    unsigned long long t0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    // (a) this rank's winner over the per-CTA candidates of the launch
+    double bv = -1.0, b2 = -1.0;
+    long long bi = MOR_IDX_NONE;
+    for (int t = tid; t < (int)gridDim.x; t += DEIM_THREADS) {
+        const double v = __ldcg(&a.cands[t].val);
+        const long long ix = __ldcg(&a.cands[t].idx);
+        const double s = __ldcg(&a.cands[t].val2);
+        cand_merge(bv, bi, b2, v, ix, s);
+    }
+    __syncthreads();   // sv/si/ss2 were used by the CTA's own reduction
+    cand_block_reduce(bv, bi, b2, sv, si, ss2);
+    if (tid == 0) {
+        widx_s = bi;
+        sbuf[0] = bv;
+        sbuf[1] = __longlong_as_double(bi);
+        sbuf[rec - 1] = b2;
+    }
+    __syncthreads();
+    // (b) the record: [value, bits(global index), U[idx, 0..k), panel row (16), sub-panel row (4), runner-up]
+    const long long g = widx_s;
+    for (int jx = tid; jx < k; jx += DEIM_THREADS)
+        sbuf[2 + jx] = (g == MOR_IDX_NONE || jx >= a.kcols) ? 0.0 : a.U[(g - a.row_offset) + (int64_t)jx * a.ldU];
+    if (a.blocked) {
+        if (tid < DEIM_BLOCK)
+            sbuf[2 + k + tid] = (g == MOR_IDX_NONE || tid >= a.bw || a.Pn == nullptr) ? 0.0 : a.Pn[(g - a.row_offset) + (int64_t)tid * a.ldn];
+        if (tid >= 32 && tid < 32 + DEIM_SUB) {
+            const int q = tid - 32;
+            sbuf[2 + k + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= a.sw || a.P2 == nullptr) ? 0.0 : a.P2[(g - a.row_offset) + (int64_t)q * a.ld2];
+        }
+    }
+    __syncthreads();
+    // (c) publish
+    const size_t slot_off = (size_t)a.slot * a.nranks * rec;
+    if (a.mode == 1) {   // NCCL fallback: the host all-gathers `send` and launches deim_tail_global_kernel
+        for (int e = tid; e < rec; e += DEIM_THREADS) a.send[e] = sbuf[e];
+        if (tid == 0) {
+            *a.ticket = 0;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            atomicAdd(a.tail_ns, t1 - t0);
+        }
+        return;
+    }
+    const size_t my_off = slot_off + (size_t)a.rank * rec;
+    for (int e = tid; e < rec; e += DEIM_THREADS) {
+        const double v = sbuf[e];
+        for (int p = 0; p < a.nranks; ++p) a.peer_box[p][my_off + e] = v;
+    }
+    if (a.nranks > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.nranks && tid != a.rank) {
+            st_release_sys(a.peer_flags[tid] + a.slot * DEIM_MAXRANKS + a.rank, a.expect);
+            const unsigned long long* f = a.flags + a.slot * DEIM_MAXRANKS + tid;
+            const long long c0 = clock64();
+            while (ld_acquire_sys(f) != a.expect) {
+                if (clock64() - c0 > (1LL << 32)) {   // ~2 s: a peer died; fail instead of hanging the GPU
+                    atomicExch(a.status, -1);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // (d) global winner, factor updates, next coefficients
+    deim_tail_global(a, a.box + slot_off, sbuf);
+    if (tid == 0) {
+        *a.ticket = 0;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        atomicAdd(a.tail_ns, t1 - t0);
+    }
+}
+
+// elect the last CTA of the grid to finish its streaming work
+__device__ __forceinline__ bool deim_last_cta(unsigned* ticket) {
+    __shared__ unsigned last_s;
+    __threadfence();
+    if (threadIdx.x == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (last_s) __threadfence();
+    return last_s != 0;
+}
+
+__global__ void __launch_bounds__(DEIM_THREADS) deim_tail_global_kernel(TailArgs a, const double* gathered) {
+    __shared__ double sbuf[SBUF_DOUBLES];
+    deim_tail_global(a, gathered, sbuf);
+}
+
+// Fused residual + abs-argmax over this rank's rows, then the tail.  l = number of previous columns.
 // VEC: 16-byte loads (needs 16B-aligned base and even ld).  Each CTA walks chunks of
 // 2*R*256 consecutive rows; for every column the CTA reads one contiguous 4*R KB run.
 template <int R, bool VEC>
 __global__ void __launch_bounds__(DEIM_THREADS)
-deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
-                 const double* __restrict__ cg, int64_t row_offset, Cand* __restrict__ out) {
-    __shared__ double sc[1024];
-    __shared__ double sv[DEIM_THREADS / 32];
-    __shared__ long long si[DEIM_THREADS / 32];
+deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l, const double* __restrict__ cg,
+                 int64_t row_offset, TailArgs ta) {
+    __shared__ double sc[SBUF_DOUBLES];   // coefficients during the streaming loop, record / LU state in the tail
+    __shared__ double sv[DEIM_WARPS], ss2[DEIM_WARPS];
+    __shared__ long long si[DEIM_WARPS];
     const int tid = threadIdx.x;
     for (int j = tid; j < l; j += DEIM_THREADS) sc[j] = cg[j];
     __syncthreads();
@@ -109,7 +374,7 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
     const int64_t CH = 2 * R * DEIM_THREADS;
     const int64_t nchunks = (m + CH - 1) / CH;
     const double* __restrict__ ul = U + (int64_t)l * ld;
-    double bv = -1.0;
+    double bv = -1.0, b2 = -1.0;
     long long bi = MOR_IDX_NONE;
 
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -154,8 +419,8 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
                 for (int r = 0; r < R; ++r) {
                     const int64_t row = c0 + 2 * tid + r * (2 * DEIM_THREADS);
                     const double2 u = ld_stream2(ul + row);
-                    cand_take(bv, bi, fabs(u.x - acc[r].x), row_offset + row);
-                    cand_take(bv, bi, fabs(u.y - acc[r].y), row_offset + row + 1);
+                    cand_take(bv, bi, b2, fabs(u.x - acc[r].x), row_offset + row);
+                    cand_take(bv, bi, b2, fabs(u.y - acc[r].y), row_offset + row + 1);
                 }
             } else {
                 double acc[2 * R];
@@ -173,7 +438,7 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
 #pragma unroll
                 for (int r = 0; r < 2 * R; ++r) {
                     const int64_t row = c0 + tid + r * DEIM_THREADS;
-                    cand_take(bv, bi, fabs(ld_stream1(ul + row) - acc[r]), row_offset + row);
+                    cand_take(bv, bi, b2, fabs(ld_stream1(ul + row) - acc[r]), row_offset + row);
                 }
             }
         } else {  // ragged last chunk
@@ -181,36 +446,40 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l,
                 double acc = 0.0;
                 const double* p = U + row;
                 for (int j = 0; j < l; ++j) acc = fma(p[(int64_t)j * ld], sc[j], acc);
-                cand_take(bv, bi, fabs(ul[row] - acc), row_offset + row);
+                cand_take(bv, bi, b2, fabs(ul[row] - acc), row_offset + row);
             }
         }
     }
-    cand_block_reduce<DEIM_THREADS / 32>(bv, bi, sv, si);
+    cand_block_reduce(bv, bi, b2, sv, si, ss2);
     if (tid == 0) {
-        out[blockIdx.x].val = bv;
-        out[blockIdx.x].idx = bi;
+        ta.cands[blockIdx.x].val = bv;
+        ta.cands[blockIdx.x].idx = bi;
+        ta.cands[blockIdx.x].val2 = b2;
     }
+    if (!deim_last_cta(ta.ticket)) return;
+    deim_tail(ta, sc, sv, si, ss2);
 }
 
 // Second blocking level: residuals of the next sw <= 4 columns of a panel P1 with respect to the s0 <= 12
 // interpolation points already chosen inside that panel,
 //     R2[:, q] = P1[:, s0 + q] - sum_{t < s0} P1[:, t] * D[t][q],
-// written to the sub-panel R2 and fused with the abs-argmax of its first column (= the next greedy step).
-// One streaming pass over s0 + sw panel columns instead of one pass per greedy step.  D: 16 x 4 column-major.
+// written to the sub-panel R2 and fused with the abs-argmax of its first column (= the next greedy step) and the
+// tail.  One streaming pass over s0 + sw panel columns instead of one pass per greedy step.  D: 16 x 4 column-major.
 template <int R>
 __global__ void __launch_bounds__(DEIM_THREADS)
 deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0, int sw, const double* __restrict__ Dg,
-                  double* __restrict__ R2, int64_t ld2, int64_t row_offset, Cand* __restrict__ out) {
-    __shared__ double sd[DEIM_BLOCK * DEIM_SUB];
-    __shared__ double sv[DEIM_THREADS / 32];
-    __shared__ long long si[DEIM_THREADS / 32];
+                  double* __restrict__ R2, int64_t ld2, int64_t row_offset, TailArgs ta) {
+    __shared__ double sbuf[SBUF_DOUBLES];
+    __shared__ double sv[DEIM_WARPS], ss2[DEIM_WARPS];
+    __shared__ long long si[DEIM_WARPS];
+    double* sd = sbuf;
     const int tid = threadIdx.x;
     if (tid < DEIM_BLOCK * DEIM_SUB) sd[tid] = Dg[tid];
     __syncthreads();
 
     const int64_t CH = 2 * R * DEIM_THREADS;
     const int64_t nchunks = (m + CH - 1) / CH;
-    double bv = -1.0;
+    double bv = -1.0, b2 = -1.0;
     long long bi = MOR_IDX_NONE;
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int64_t c0 = chunk * CH;
@@ -247,8 +516,8 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
                         const double2 res = make_double2(u.x - acc[r][q].x, u.y - acc[r][q].y);
                         *reinterpret_cast<double2*>(R2 + (int64_t)q * ld2 + row) = res;
                         if (q == 0) {
-                            cand_take(bv, bi, fabs(res.x), row_offset + row);
-                            cand_take(bv, bi, fabs(res.y), row_offset + row + 1);
+                            cand_take(bv, bi, b2, fabs(res.x), row_offset + row);
+                            cand_take(bv, bi, b2, fabs(res.y), row_offset + row + 1);
                         }
                     }
                 }
@@ -268,68 +537,20 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
                     if (q < sw) {
                         const double res = p[(int64_t)(s0 + q) * ld1] - acc[q];
                         R2[(int64_t)q * ld2 + row] = res;
-                        if (q == 0) cand_take(bv, bi, fabs(res), row_offset + row);
+                        if (q == 0) cand_take(bv, bi, b2, fabs(res), row_offset + row);
                     }
                 }
             }
         }
     }
-    cand_block_reduce<DEIM_THREADS / 32>(bv, bi, sv, si);
+    cand_block_reduce(bv, bi, b2, sv, si, ss2);
     if (tid == 0) {
-        out[blockIdx.x].val = bv;
-        out[blockIdx.x].idx = bi;
+        ta.cands[blockIdx.x].val = bv;
+        ta.cands[blockIdx.x].idx = bi;
+        ta.cands[blockIdx.x].val2 = b2;
     }
-}
-
-// D (16 x 4 column-major, zero padded) = Zb[0:s0, 0:s0] * Ufb[0:s0, s0 : s0+sw] from the panel's own factors
-// (row-major with stride kb): column q solves (P'P1_s0) d = P'P1[:, s0+q].
-__global__ void __launch_bounds__(DEIM_BLOCK * DEIM_SUB)
-deim_sub_coef_kernel(const double* __restrict__ Zb, const double* __restrict__ Ufb, int kb, int s0, int sw,
-                     double* __restrict__ D) {
-    const int t = threadIdx.x % DEIM_BLOCK, q = threadIdx.x / DEIM_BLOCK;
-    double s = 0.0;
-    if (t < s0 && q < sw)
-        for (int r = t; r < s0; ++r) s = fma(Zb[t * kb + r], Ufb[r * kb + s0 + q], s);
-    D[q * DEIM_BLOCK + t] = s;
-}
-
-// Reduce the per-CTA candidates of this rank and gather the winner's basis row:
-// send = [value, bits(global index), U[idx, 0..k)]
-// (blocked path: followed by the winner's row of the current residual panel, Pn[idx, 0..bw), padded to 16)
-__global__ void __launch_bounds__(1024)
-deim_local_kernel(const Cand* __restrict__ cands, int ncand, const double* __restrict__ U, int64_t ld,
-                  int64_t row_offset, int k, double* __restrict__ send, const double* __restrict__ Pn,
-                  int64_t ldp, int bw, const double* __restrict__ P2, int64_t ld2, int sw, int kcols) {
-    __shared__ double sv[32];
-    __shared__ long long si[32];
-    __shared__ long long widx;
-    double bv = -1.0;
-    long long bi = MOR_IDX_NONE;
-    for (int t = threadIdx.x; t < ncand; t += 1024) {
-        const double v = cands[t].val;
-        const long long i = cands[t].idx;
-        if (cand_better(v, i, bv, bi)) {
-            bv = v;
-            bi = i;
-        }
-    }
-    cand_block_reduce<32>(bv, bi, sv, si);
-    if (threadIdx.x == 0) {
-        widx = bi;
-        send[0] = bv;
-        send[1] = __longlong_as_double(bi);
-    }
-    __syncthreads();
-    const long long g = widx;
-    for (int j = threadIdx.x; j < k; j += 1024)
-        send[2 + j] = (g == MOR_IDX_NONE || j >= kcols) ? 0.0 : U[(g - row_offset) + (int64_t)j * ld];   // later columns: deferred
-    if (Pn != nullptr && threadIdx.x < DEIM_BLOCK)
-        send[2 + k + threadIdx.x] =
-            (g == MOR_IDX_NONE || (int)threadIdx.x >= bw) ? 0.0 : Pn[(g - row_offset) + (int64_t)threadIdx.x * ldp];
-    if (P2 != nullptr && threadIdx.x >= 32 && threadIdx.x < 32 + DEIM_SUB) {
-        const int q = threadIdx.x - 32;
-        send[2 + k + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= sw) ? 0.0 : P2[(g - row_offset) + (int64_t)q * ld2];
-    }
+    if (!deim_last_cta(ta.ticket)) return;   // includes the fence that publishes this CTA's R2 stores
+    deim_tail(ta, sbuf, sv, si, ss2);
 }
 
 __device__ __forceinline__ double warp_sum(double s) {
@@ -338,66 +559,23 @@ __device__ __forceinline__ double warp_sum(double s) {
     return s;
 }
 
-// Replicated on every rank: choose the global winner, append its row to W = P'U (row i),
-// extend the LU factors (L row i, U-factor row i, Z column i) and compute the coefficient
-// vector c (length i+1) of the NEXT step.  All k x k arrays are row-major with stride k; Zt is
-// the transpose of Z, kept so that every phase reads with the output index contiguous.
-// Every phase is a (triangular) matrix-vector product: thread (x, y) accumulates the terms
-// t = y (mod ways) of output x, the `ways` partial sums are combined through shared memory --
-// a sequential depth of k / ways instead of k on this latency-critical single-CTA kernel.
-struct UpdState {
-    double *Wm, *Uf, *Lm, *Z, *Zt, *c;   // k x k row-major (stride k) factors and the next coefficient vector
-    long long* idx_out;                  // selected indices (1-based) or nullptr
-    int i, k;                            // step (row being appended) and dimension of this state
-    int rowoff;                          // offset of this state's row inside a gathered record
-    int last;                            // 1: the final greedy step (a zero pivot no longer matters)
-    int jmax;                            // U-factor row i is formed for columns [i, jmax) (k unless later columns are deferred)
-};
-struct UpdArgs {
-    UpdState st[2];                      // blockIdx.x selects: 0 = P'U of the basis, 1 = P'R of the current panel
-};
-
+// ---- streaming path: bordered LU of the k x k block P'U, one row per greedy step -----------------------------
+// Replicated on every rank: append row i of W = P'U (already stored by the tail), extend the LU factors (L row i,
+// U-factor row i, Z column i) and compute the coefficient vector c (length i+1) of the NEXT step.  All k x k arrays
+// are row-major with stride k; Zt is the transpose of Z, kept so that every phase reads with the output index
+// contiguous.  Every phase is a (triangular) matrix-vector product: thread (x, y) accumulates the terms
+// t = y (mod ways) of output x, the `ways` partial sums are combined through shared memory -- a sequential depth of
+// k / ways instead of k on this latency-critical single-CTA kernel.
 __global__ void __launch_bounds__(1024)
-deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, UpdArgs args, int* __restrict__ status) {
-    const UpdState& S = args.st[blockIdx.x];
-    const int i = S.i, k = S.k;
-    double* __restrict__ Wm = S.Wm;
-    double* __restrict__ Uf = S.Uf;
-    double* __restrict__ Lm = S.Lm;
-    double* __restrict__ Z = S.Z;
-    double* __restrict__ Zt = S.Zt;
-    double* __restrict__ c = S.c;
-    long long* __restrict__ idx_out = S.idx_out;
+deim_update_kernel(const double* __restrict__ Wm, double* __restrict__ Uf, double* __restrict__ Lm, double* __restrict__ Z,
+                   double* __restrict__ Zt, double* __restrict__ c, int i, int k, int last, int* __restrict__ status) {
     __shared__ double w[1024], ell[1024], ucol[1024], y[1024], part[1024];
-    __shared__ int win_s;
     const int tid = threadIdx.x;
     const int KP = (k + 31) & ~31;       // outputs per phase, padded to whole warps
     const int ways = 1024 / KP;          // reduction split (k <= 1024 => ways >= 1)
     const int x = tid % KP, yy = tid / KP;
     const bool active = yy < ways;
-    if (tid == 0) {
-        int win = 0;
-        double bv = -1.0;
-        long long bi = MOR_IDX_NONE;
-        for (int r = 0; r < nranks; ++r) {
-            const double v = gathered[(size_t)r * stride];
-            const long long ix = __double_as_longlong(gathered[(size_t)r * stride + 1]);
-            if (cand_better(v, ix, bv, bi)) {
-                bv = v;
-                bi = ix;
-                win = r;
-            }
-        }
-        win_s = win;
-        if (idx_out != nullptr) idx_out[i] = bi + 1;  // 1-based, like Julia
-    }
-    __syncthreads();
-    const double* src = gathered + (size_t)win_s * stride + S.rowoff;
-    for (int j = tid; j < k; j += 1024) {
-        const double v = src[j];
-        w[j] = v;
-        Wm[(size_t)i * k + j] = v;
-    }
+    for (int j = tid; j < k; j += 1024) w[j] = Wm[(size_t)i * k + j];
     __syncthreads();
     // combine the `ways` partial sums of output x (valid in threads with yy == 0)
     auto combine = [&](double s) -> double {
@@ -427,18 +605,18 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
     {
         const int j = i + x;
         double s = 0.0;
-        if (active && j < S.jmax) {
+        if (active && j < k) {
 #pragma unroll 8
             for (int t = yy; t < i; t += ways) s = fma(ell[t], __ldcg(&Uf[(size_t)t * k + j]), s);
         }
         s = combine(s);
-        if (yy == 0 && j < S.jmax) Uf[(size_t)i * k + j] = w[j] - s;
+        if (yy == 0 && j < k) Uf[(size_t)i * k + j] = w[j] - s;
     }
     __syncthreads();
     for (int t = tid; t < i; t += 1024) ucol[t] = Uf[(size_t)t * k + i];
     __syncthreads();
     const double pivot = Uf[(size_t)i * k + i];
-    if (tid == 0 && pivot == 0.0 && !S.last && idx_out != nullptr && *status == 0) *status = i + 1;
+    if (tid == 0 && pivot == 0.0 && !last && *status == 0) *status = i + 1;
     // Z column i:  Z[r][i] = -(sum_{t=r}^{i-1} Z[r][t] * Uf[t][i]) / pivot,  r < i;  Z[i][i] = 1/pivot
     {
         double s = 0.0;
@@ -453,7 +631,7 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
             Zt[(size_t)i * k + x] = z;
         }
     }
-    if (i + 1 >= S.jmax) return;
+    if (i + 1 >= k) return;
     __syncthreads();
     for (int t = tid; t <= i; t += 1024) y[t] = Uf[(size_t)t * k + i + 1];
     __syncthreads();
@@ -469,55 +647,122 @@ deim_update_kernel(const double* __restrict__ gathered, int nranks, int stride, 
     }
 }
 
-// Deferred columns (pipelined host ingest: the basis arrives 16 columns at a time, so the rows of the points
-// chosen so far cannot be gathered beyond the columns that have landed).  At the panel boundary l1:
-//   deim_gather_block_kernel   W12[t][q] = U[idx[t], l1 + q], t < l1 (zero for rows of other ranks; all-reduced)
-//   deim_fwd_subst_kernel      Uf[0:l1, l1 + q] = inv(L[0:l1, 0:l1]) * W12[:, q]  (unit lower L, one warp per column q)
-// which is what the per-step bordered update would have left in those columns of the U-factor.
+// ---- blocked path: A = inv(P'U) kept explicitly, extended once per panel ----------------------------------------
+// Pipelined host ingest: the basis arrives 16 columns at a time, so the rows of the points chosen so far cannot be
+// gathered beyond the columns that have landed.  At the panel boundary l0:
+//   W12[t][q] = U[idx[t], l0 + q], t < l0   (zero for rows of other ranks; all-reduced by the host)
 __global__ void __launch_bounds__(128)
 deim_gather_block_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset,
-                         const long long* __restrict__ idx, int l1, int bw, double* __restrict__ W12) {
+                         const long long* __restrict__ idx, int l0, int bw, double* __restrict__ W12) {
     const int t = blockIdx.x * 8 + threadIdx.x / DEIM_BLOCK, q = threadIdx.x % DEIM_BLOCK;
-    if (t >= l1) return;
+    if (t >= l0) return;
     const long long loc = idx[t] - 1 - row_offset;
-    W12[t * DEIM_BLOCK + q] = (loc >= 0 && loc < m && q < bw) ? U[loc + (int64_t)(l1 + q) * ld] : 0.0;
+    W12[t * DEIM_BLOCK + q] = (loc >= 0 && loc < m && q < bw) ? U[loc + (int64_t)(l0 + q) * ld] : 0.0;
 }
 
-__global__ void __launch_bounds__(32 * DEIM_BLOCK)
-deim_fwd_subst_kernel(const double* __restrict__ Lm, const double* __restrict__ W12, int k, int l1, int bw,
-                      double* Uf) {
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (q >= bw) return;
-    double* y = Uf + l1 + q;                      // y[t * k] = Uf[t][l1 + q]
-    for (int t = 0; t < l1; ++t) {
-        double s = 0.0;
-        for (int r = lane; r < t; r += 32) s = fma(__ldcg(&Lm[(size_t)t * k + r]), __ldcg(&y[(size_t)r * k]), s);
-        s = warp_sum(s);
-        if (lane == 0) y[(size_t)t * k] = W12[t * DEIM_BLOCK + q] - s;
-        __syncwarp();
-    }
-}
-
-// Coefficients of the next panel, packed for deim_panel_kernel: C = Z[0:l1, 0:l1] * Uf[0:l1, l1 : l1+bw]
-// (Uf[:, j] = inv(L) P'u_j is already part of the U-factor, Z = inv(Uf[0:l1, 0:l1])), i.e. column q of C
-// solves (P'U_l1) c = P'u_{l1+q}, deim.jl:21.  One CTA per 16-row slab: Cp[c][q][kk] = C[16 c + kk][q].
+// Coefficients of the panel that starts at column l0:  C = A[0:l0, 0:l0] * W12  (column q of C solves
+// (P'U_l0) c = P'u_{l0+q}, deim.jl:21).  W12[s][q] = Wsrc[s * ldw + q].  One CTA per 16-row slab; written twice:
+// packed for deim_panel_kernel, Cp[c][q][kk] = C[16 c + kk][q], and plain (C12[t * 16 + q]) for the panel-end update.
 __global__ void __launch_bounds__(DEIM_BLOCK * 20)
-deim_block_coef_kernel(const double* __restrict__ Z, const double* __restrict__ Uf, int k, int l1, int bw,
-                       double* __restrict__ Cp) {
+deim_coef_kernel(const double* __restrict__ A, int k, int l0, int bw, const double* __restrict__ Wsrc, int ldw,
+                 double* __restrict__ Cp, double* __restrict__ C12) {
     const int e = threadIdx.x, q = e / 20, kk = e % 20;
     const int t = blockIdx.x * DEIM_BLOCK + kk;
-    double s0 = 0.0, s1 = 0.0;
-    if (kk < DEIM_BLOCK && q < bw && t < l1) {
-        const double* z = Z + (size_t)t * k;
-        const double* u = Uf + l1 + q;
-        int r = t;
-        for (; r + 2 <= l1; r += 2) {
-            s0 = fma(z[r], u[(size_t)r * k], s0);
-            s1 = fma(z[r + 1], u[(size_t)(r + 1) * k], s1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (kk < DEIM_BLOCK && q < bw && t < l0) {
+        const double* a = A + (size_t)t * k;
+        const double* w = Wsrc + q;
+        int r = 0;
+        for (; r + 4 <= l0; r += 4) {
+            s0 = fma(a[r], w[(size_t)r * ldw], s0);
+            s1 = fma(a[r + 1], w[(size_t)(r + 1) * ldw], s1);
+            s2 = fma(a[r + 2], w[(size_t)(r + 2) * ldw], s2);
+            s3 = fma(a[r + 3], w[(size_t)(r + 3) * ldw], s3);
         }
-        if (r < l1) s0 = fma(z[r], u[(size_t)r * k], s0);
+        for (; r < l0; ++r) s0 = fma(a[r], w[(size_t)r * ldw], s0);
     }
-    Cp[(size_t)blockIdx.x * (DEIM_BLOCK * 20) + e] = s0 + s1;
+    const double v = (s0 + s1) + (s2 + s3);
+    Cp[(size_t)blockIdx.x * (DEIM_BLOCK * 20) + e] = v;
+    if (kk < DEIM_BLOCK && t < l0) C12[t * DEIM_BLOCK + q] = v;
+}
+
+// Panel end, step 1: Sinv = inv(S) = Z * inv(L) of the panel's pivot block S = P'R = L * Uf (16 x 16, unit lower L),
+// and the new diagonal block A[l0:l0+bw, l0:l0+bw] = Sinv.
+__global__ void __launch_bounds__(DEIM_BLOCK * DEIM_BLOCK)
+deim_sinv_kernel(const double* __restrict__ bst, int bw, int k, int l0, double* __restrict__ Sinv, double* __restrict__ A) {
+    __shared__ double L[DEIM_BLOCK * DEIM_BLOCK], Z[DEIM_BLOCK * DEIM_BLOCK], Li[DEIM_BLOCK * DEIM_BLOCK];
+    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK;
+    const int tid = threadIdx.x, a = tid / DEIM_BLOCK, b = tid % DEIM_BLOCK;
+    L[tid] = bst[BB + tid];
+    Z[tid] = bst[2 * BB + tid];
+    Li[tid] = a == b ? 1.0 : 0.0;
+    __syncthreads();
+    if (tid < bw) {   // column tid of inv(L) by forward substitution (L unit lower; strictly lower part stored)
+        const int cc = tid;
+        for (int r = cc + 1; r < bw; ++r) {
+            double s = 0.0;
+            for (int t = cc; t < r; ++t) s = fma(L[r * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + cc], s);
+            Li[r * DEIM_BLOCK + cc] = -s;
+        }
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (a < bw && b < bw)
+        for (int t = (a > b ? a : b); t < bw; ++t) s = fma(Z[a * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + b], s);
+    Sinv[tid] = s;
+    if (a < bw && b < bw) A[(size_t)(l0 + a) * k + l0 + b] = s;
+}
+
+// Panel end, step 2: F = Sinv * (W21 * A11)  (bw x l0), W21 = W[l0:l0+bw, 0:l0]; also A21 = -F.
+// One thread per column j of A11; W21 is staged through shared memory in chunks of 64 rows of A.
+__global__ void __launch_bounds__(64)
+deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W, int k, int l0, int bw,
+                  const double* __restrict__ Sinv, double* __restrict__ F) {
+    __shared__ double w21[DEIM_BLOCK][64], sinv[DEIM_BLOCK * DEIM_BLOCK];
+    const int tid = threadIdx.x, j = blockIdx.x * 64 + tid;
+    for (int e = tid; e < DEIM_BLOCK * DEIM_BLOCK; e += 64) sinv[e] = Sinv[e];
+    double acc[DEIM_BLOCK];
+#pragma unroll
+    for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = 0.0;
+    for (int t0 = 0; t0 < l0; t0 += 64) {
+        __syncthreads();
+        for (int c = 0; c < DEIM_BLOCK; ++c)
+            w21[c][tid] = (c < bw && t0 + tid < l0) ? W[(size_t)(l0 + c) * k + t0 + tid] : 0.0;
+        __syncthreads();
+        const int tn = l0 - t0 < 64 ? l0 - t0 : 64;
+        if (j < l0)
+            for (int t = 0; t < tn; ++t) {
+                const double av = A[(size_t)(t0 + t) * k + j];
+#pragma unroll
+                for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = fma(w21[c][t], av, acc[c]);
+            }
+    }
+    if (j >= l0) return;
+    for (int c = 0; c < bw; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < DEIM_BLOCK; ++c2) s = fma(sinv[c * DEIM_BLOCK + c2], acc[c2], s);
+        F[(size_t)c * k + j] = s;
+        A[(size_t)(l0 + c) * k + j] = -s;
+    }
+}
+
+// Panel end, step 3: A11 += C12 * F (rank-bw update), A12 = -C12 * Sinv.  One thread per entry of the l0 x (l0 + bw) block.
+__global__ void __launch_bounds__(256)
+deim_inv_update_kernel(double* __restrict__ A, int k, int l0, int bw, const double* __restrict__ C12,
+                       const double* __restrict__ F, const double* __restrict__ Sinv) {
+    const int s = blockIdx.x * 16 + (threadIdx.x & 15), t = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (t >= l0 || s >= l0 + bw) return;
+    const double* c = C12 + t * DEIM_BLOCK;
+    double acc = 0.0;
+    if (s < l0) {
+        for (int q = 0; q < bw; ++q) acc = fma(c[q], F[(size_t)q * k + s], acc);
+        A[(size_t)t * k + s] += acc;
+    } else {
+        const int cc = s - l0;
+        for (int q = 0; q < bw; ++q) acc = fma(c[q], Sinv[q * DEIM_BLOCK + cc], acc);
+        A[(size_t)t * k + s] = -acc;
+    }
 }
 
 // MOR_B200_DEIM_BLOCK=0 selects the streaming path (one pass over columns 1..l per greedy step, the
@@ -526,13 +771,21 @@ static bool deim_blocked_enabled() {
     const char* e = getenv("MOR_B200_DEIM_BLOCK");
     return !(e && e[0] == '0');
 }
+// Below this relative gap between the best and the second-best residual a greedy step of the BLOCKED path counts as
+// a near-tie: its panel-wise arithmetic rounds differently from deim.jl:21-23, so the call is repeated with the
+// streaming path (the reference's own formulation).  Default 32 k eps: what two summation orders of the k-term dot
+// product of deim.jl:22 can differ by (measured: bench.py `deim.independent_check.residual_discrepancy`).
+// MOR_B200_DEIM_TIE_FALLBACK=0 disables, MOR_B200_DEIM_TIE_TOL sets an absolute value.
+static double deim_tie_tol(int64_t k) {
+    const char* off = getenv("MOR_B200_DEIM_TIE_FALLBACK");
+    if (off && off[0] == '0') return -1.0;
+    const char* e = getenv("MOR_B200_DEIM_TIE_TOL");
+    return e ? atof(e) : 32.0 * (double)k * 2.220446049250313e-16;
+}
 
-int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host,
-                            const cudaEvent_t* col_ready, int group_cols) {
+static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host, const cudaEvent_t* col_ready,
+                        int group_cols, bool allow_blocked) {
     Ctx& cx = ctx();
-    MOR_ARG(B != nullptr && idx_host != nullptr, "deim_interpolation_indices: null pointer");
-    MOR_ARG(k >= 1 && k <= 1024, "deim_interpolation_indices: number of basis columns must be in 1..1024");
-    MOR_ARG(m >= 0 && ld >= (m > 0 ? m : 1), "deim_interpolation_indices: bad m / ld");
     for (double& t : cx.timings) t = 0.0;
 
     std::vector<int64_t> all_m;
@@ -543,6 +796,7 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         m_global += all_m[r];
     }
     MOR_ARG(m_global >= 1, "deim_interpolation_indices: empty basis");
+    MOR_ARG(cx.nranks <= DEIM_MAXRANKS, "deim_interpolation_indices: more than 8 ranks");
 
     constexpr int R = 4;
     const int64_t CH = 2 * R * DEIM_THREADS;
@@ -555,9 +809,9 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
     // from ONE pass over the earlier columns (deim_panel_kernel); the greedy steps inside a block run the
     // same streaming kernel on that 16-column residual panel -- about 8 m k (k / 32 + 18) bytes of traffic
     // instead of 4 m k (k + 1).  It needs a 16-byte aligned basis with an even leading dimension (bulk
-    // copies) and 128 m bytes of workspace; every rank must take the same path (the gathered records differ).
+    // copies) and 160 m bytes of workspace; every rank must take the same path (the gathered records differ).
     const int64_t ldp = (m + 1) & ~int64_t(1);
-    bool blocked = deim_blocked_enabled() && k > DEIM_BLOCK && (m == 0 || (vec && ld >= ldp));
+    bool blocked = allow_blocked && deim_blocked_enabled() && k > DEIM_BLOCK && (m == 0 || (vec && ld >= ldp));
     DevBuf panel;
     if (blocked && m > 0 && panel.alloc(sizeof(double) * (size_t)ldp * (DEIM_BLOCK + DEIM_SUB)) != MOR_OK) {
         cudaGetLastError();   // no room for the panel: the streaming path needs no workspace
@@ -569,57 +823,84 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         for (int64_t v : votes) blocked = blocked && v != 0;
         if (!blocked) panel.release();
     }
+    MOR_TRY(deim_mailbox());            // own mailbox (+ peers' over NVLink when every rank could map them)
+    const bool fused = cx.nranks == 1 || cx.peers_ok;
 
     const size_t kk = (size_t)k * k;
-    // gathered record: value, index, basis row, panel row (16), sub-panel row (4)
-    const int rec = (int)k + 2 + (blocked ? DEIM_BLOCK + DEIM_SUB : 0);
-    DevBuf state, cands, xfer;
-    // state: Wm, Uf, Lm, Z, Zt (k*k each), c (k), idx (k int64), status; block state: 5 * 16*16 + 16; packed C
-    // block state 5 * 16*16 + 16, sub-block state 5 * 4*4 + 4, sub-panel coefficients D 16 x 4
-    const size_t bdoubles = 5 * DEIM_BLOCK * DEIM_BLOCK + DEIM_BLOCK + 5 * DEIM_SUB * DEIM_SUB + DEIM_SUB +
-                            DEIM_BLOCK * DEIM_SUB;
-    const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20 + (size_t)k * DEIM_BLOCK;
-    MOR_TRY(state.alloc(sizeof(double) * (5 * kk + k + bdoubles + cp_doubles) + sizeof(long long) * k + 16));
+    // gathered record: value, index, basis row, [panel row (16), sub-panel row (4)], runner-up
+    const int rec = (int)k + 3 + (blocked ? DEIM_BLOCK + DEIM_SUB : 0);
+    DevBuf state, cands;
+    // state: W (k*k); blocked: A (k*k), F (16 k), C12 (16 k), W12 (16 k), packed Cp, Sinv, bst, sst, Dsub;
+    //        streaming: Uf, L, Z, Zt (k*k each), c (k); both: margins (k), idx (k int64), status
+    const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
+    const size_t small_doubles = DEIM_BLOCK * DEIM_BLOCK + BST_DOUBLES + SST_DOUBLES + DEIM_BLOCK * DEIM_SUB;
+    const size_t ndoubles = kk + (blocked ? kk + 3 * (size_t)k * DEIM_BLOCK + cp_doubles + small_doubles : 4 * kk + (size_t)k) + 2 * (size_t)k;
+    MOR_TRY(state.alloc(sizeof(double) * ndoubles + sizeof(long long) * (size_t)k + 64));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
-    // one record slot per greedy step: the update of the k x k factors (blocked path: on the side stream) may
-    // still be reading step i's record while step i+1's is being written
-    const size_t slot = (size_t)rec * (size_t)(cx.nranks + 1);
-    MOR_TRY(xfer.alloc(sizeof(double) * slot * (size_t)(blocked ? k : 1)));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
-    double* Wm = state.as<double>();
-    double* Uf = Wm + kk;
-    double* Lm = Uf + kk;
-    double* Z = Lm + kk;
-    double* Zt = Z + kk;
-    double* c = Zt + kk;
-    double* bst = c + k;                  // block state
-    double* Cp = bst + bdoubles;          // packed panel coefficients
-    long long* idx_d = reinterpret_cast<long long*>(Cp + cp_doubles);
+    double* W = state.as<double>();
+    double* p = W + kk;
+    double *A = nullptr, *Fm = nullptr, *C12 = nullptr, *W12 = nullptr, *Cp = nullptr, *Sinv = nullptr, *bst = nullptr,
+           *sst = nullptr, *Dsub = nullptr, *Uf = nullptr, *Lm = nullptr, *Z = nullptr, *Zt = nullptr, *c = nullptr;
+    if (blocked) {
+        A = p; p += kk;
+        Fm = p; p += (size_t)k * DEIM_BLOCK;
+        C12 = p; p += (size_t)k * DEIM_BLOCK;
+        W12 = p; p += (size_t)k * DEIM_BLOCK;
+        Cp = p; p += cp_doubles;
+        Sinv = p; p += DEIM_BLOCK * DEIM_BLOCK;
+        bst = p; p += BST_DOUBLES;
+        sst = p; p += SST_DOUBLES;
+        Dsub = p; p += DEIM_BLOCK * DEIM_SUB;
+    } else {
+        Uf = p; p += kk;
+        Lm = p; p += kk;
+        Z = p; p += kk;
+        Zt = p; p += kk;
+        c = p; p += k;
+    }
+    double* margins_d = p; p += k;
+    double* values_d = p; p += k;
+    long long* idx_d = reinterpret_cast<long long*>(p);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
-    const size_t bb = (size_t)DEIM_BLOCK * DEIM_BLOCK, ss = (size_t)DEIM_SUB * DEIM_SUB;
-    double* sst = bst + 5 * bb + DEIM_BLOCK;        // sub-block state
-    double* Dsub = sst + 5 * ss + DEIM_SUB;         // sub-panel coefficients
+    unsigned long long* tail_ns_d = reinterpret_cast<unsigned long long*>(status_d + 2);
     double* R2 = blocked && m > 0 ? panel.as<double>() + (size_t)ldp * DEIM_BLOCK : nullptr;
-    double* W12 = Cp + (cp_doubles - (size_t)k * DEIM_BLOCK);   // deferred columns of the chosen rows (k x 16)
-    // pipelined ingest: later columns of the basis are not there yet, so the k x k update is confined to the
-    // columns of the current panel and the rest is caught up at each panel boundary
+    // pipelined ingest: later columns of the basis are not there yet, so a record carries the winner's row only up
+    // to the current panel and the rest is gathered at each panel boundary
     const bool defer = blocked && col_ready != nullptr;
     if (!blocked && col_ready != nullptr)
         for (int g = 0; g * group_cols < (int)k; ++g) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[g], 0));
-    // Blocked path: inside a block only the 16 x 16 factors of the panel decide the next coefficients, so the
-    // (much longer) bordered update of the k x k factors runs on a side stream, off the per-step latency chain;
-    // the main stream joins it at the next block boundary, where the panel coefficients need Z and Uf.
-    cudaEvent_t ev_rec = nullptr, ev_side = nullptr;
-    if (blocked) {
-        if (!cx.copy_stream) MOR_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
-        MOR_CUDA(cudaEventCreateWithFlags(&ev_rec, cudaEventDisableTiming));
-        MOR_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
-        MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));          // the memset above
-        MOR_CUDA(cudaStreamWaitEvent(cx.copy_stream, ev_rec, 0));
-    }
-    cudaStream_t side = blocked ? cx.copy_stream : cx.stream;
 
-    Timer t_total(MOR_T_TOTAL), t_step(MOR_T_DEIM_STEP), t_tail(MOR_T_DEIM_TAIL), t_panel(MOR_T_DEIM_PANEL);
+    TailArgs ta{};
+    ta.ticket = cx.box_ticket;
+    ta.cands = cands.as<Cand>();
+    ta.U = B;
+    ta.ldU = ld;
+    ta.k = (int)k;
+    ta.row_offset = row_offset;
+    ta.box = cx.box;
+    ta.flags = cx.box_flags;
+    for (int r = 0; r < cx.nranks; ++r) {
+        ta.peer_box[r] = fused ? cx.peer_box[r] : cx.box;
+        ta.peer_flags[r] = fused ? cx.peer_flags[r] : cx.box_flags;
+    }
+    ta.send = cx.box + (size_t)DEIM_SLOTS * DEIM_MAXRANKS * DEIM_REC_MAX;
+    ta.rank = cx.rank;
+    ta.nranks = cx.nranks;
+    ta.rec = rec;
+    ta.mode = fused ? 0 : 1;
+    ta.W = W;
+    ta.idx_out = idx_d;
+    ta.margins = margins_d;
+    ta.values = values_d;
+    ta.blocked = blocked ? 1 : 0;
+    ta.bst = bst;
+    ta.sst = sst;
+    ta.Dsub = Dsub;
+    ta.status = status_d;
+    ta.tail_ns = tail_ns_d;
+
+    Timer t_total(MOR_T_TOTAL), t_panel(MOR_T_DEIM_PANEL), t_upd(MOR_T_DEIM_UPDATE);
     t_total.start();
     for (int i = 0; i < (int)k; ++i) {
         const int l0 = blocked ? (i / DEIM_BLOCK) * DEIM_BLOCK : 0;   // first column of the current block
@@ -634,91 +915,133 @@ int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, i
         const int sw = blocked ? (bw - s0 < DEIM_SUB ? bw - s0 : DEIM_SUB) : 0;
         const double* P2 = (blocked && s0 > 0) ? R2 : Pn + (size_t)s0 * ldn;
         const int64_t ld2 = (blocked && s0 > 0) ? ldp : ldn;
-        double* send = xfer.as<double>() + (blocked ? slot * (size_t)i : 0);
-        double* gathered = cx.nranks > 1 ? send + rec : send;
         // pipelined host ingest: columns [i, i + group_cols) are first touched by this step (the panel of a
         // block reads columns < l0 + 16 and DEIM_BLOCK == group_cols; the streaming step i reads columns <= i)
-        if (defer && col_ready != nullptr && i % group_cols == 0)
-            MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[i / group_cols], 0));
+        if (defer && i % group_cols == 0) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[i / group_cols], 0));
         if (blocked && j == 0 && l0 > 0) {
-            MOR_CUDA(cudaEventRecord(ev_side, side));       // all earlier updates of the k x k factors
-            MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
-            t_panel.start();
+            t_upd.start();
+            const double* wsrc = W + l0;
+            int ldw = (int)k;
             if (defer) {
                 deim_gather_block_kernel<<<(l0 + 7) / 8, 128, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, W12);
+                count_launch();
                 if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W12, (size_t)l0 * DEIM_BLOCK));
-                deim_fwd_subst_kernel<<<1, 32 * DEIM_BLOCK, 0, cx.stream>>>(Lm, W12, (int)k, l0, bw, Uf);
-                count_launch(2);
+                wsrc = W12;
+                ldw = DEIM_BLOCK;
             }
-            deim_block_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(Z, Uf, (int)k, l0, bw, Cp);
+            deim_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(A, (int)k, l0, bw, wsrc, ldw, Cp, C12);
             count_launch();
+            t_upd.stop();
+            t_panel.start();
             if (m > 0) MOR_TRY(deim_panel(B, ld, l0, bw, Cp, m, panel.as<double>(), ldp));
             t_panel.stop();
         }
-        t_step.start();
+        ta.i = i;
+        ta.kcols = defer ? l0 + bw : (int)k;
+        ta.Pn = blocked && m > 0 ? Pn : nullptr;
+        ta.ldn = ldn;
+        ta.bw = bw;
+        ta.P2 = blocked && m > 0 ? P2 : nullptr;
+        ta.ld2 = ld2;
+        ta.sw = sw;
+        ta.j = j;
+        ta.jj = jj;
+        ta.s0 = s0;
+        ta.last = i == (int)k - 1 ? 1 : 0;
+        const unsigned long long seq = cx.deim_seq + (unsigned long long)i;
+        ta.slot = (int)(seq % DEIM_SLOTS);
+        ta.expect = seq + 1;
         if (blocked && s0 > 0 && jj == 0) {
             // residuals of the next 4 panel columns in one pass over the s0 earlier ones, fused with this step's argmax
-            deim_sub_coef_kernel<<<1, DEIM_BLOCK * DEIM_SUB, 0, cx.stream>>>(bst + 3 * bb, bst + bb, bw, s0, sw, Dsub);
-            deim_step4_kernel<R><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, s0, sw, Dsub, R2, ldp, row_offset,
-                                                                       cands.as<Cand>());
-            count_launch();
+            deim_step4_kernel<R><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, s0, sw, Dsub, R2, ldp, row_offset, ta);
         } else if (blocked) {
-            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(P2, m, ld2, jj, sst + 5 * ss, row_offset,
-                                                                            cands.as<Cand>());
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(P2, m, ld2, jj, sst + 3 * DEIM_SUB * DEIM_SUB,
+                                                                            row_offset, ta);
         } else if (vec) {
-            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, ta);
         } else {
-            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, cands.as<Cand>());
+            deim_step_kernel<R, false><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, ta);
         }
-        t_step.stop();
-        t_tail.start();
-        deim_local_kernel<<<1, 1024, 0, cx.stream>>>(cands.as<Cand>(), grid, B, ld, row_offset, (int)k, send,
-                                                     blocked ? Pn : nullptr, ldn, bw, blocked ? P2 : nullptr, ld2, sw,
-                                                     defer ? l0 + bw : (int)k);
-        if (cx.nranks > 1) MOR_TRY(comm_allgather(send, gathered, sizeof(double) * (size_t)rec));
-        UpdArgs ua;
-        ua.st[0] = UpdState{Wm, Uf, Lm, Z, Zt, c, idx_d, i, (int)k, 2, i == (int)k - 1 ? 1 : 0, defer ? l0 + bw : (int)k};
-        ua.st[1] = ua.st[0];
-        if (blocked) {
-            MOR_CUDA(cudaEventRecord(ev_rec, cx.stream));   // record i is complete
-            MOR_CUDA(cudaStreamWaitEvent(side, ev_rec, 0));
-            deim_update_kernel<<<1, 1024, 0, side>>>(gathered, cx.nranks, rec, ua, status_d);
-            UpdArgs ub;   // the panel's 16 x 16 factors and the sub-panel's 4 x 4 factors: two CTAs of one launch
-            ub.st[0] = UpdState{bst, bst + bb, bst + 2 * bb, bst + 3 * bb, bst + 4 * bb, bst + 5 * bb, nullptr, j, bw,
-                                2 + (int)k, 1, bw};
-            ub.st[1] = UpdState{sst, sst + ss, sst + 2 * ss, sst + 3 * ss, sst + 4 * ss, sst + 5 * ss, nullptr, jj, sw,
-                                2 + (int)k + DEIM_BLOCK, 1, sw};
-            deim_update_kernel<<<2, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ub, status_d);
-            count_launch(4);
-        } else {
-            deim_update_kernel<<<1, 1024, 0, cx.stream>>>(gathered, cx.nranks, rec, ua, status_d);
-            count_launch(3);
+        count_launch();
+        if (!fused) {   // NCCL fallback: all-gather the records, then the global part of the tail as its own launch
+            double* gathered = cx.box + (size_t)ta.slot * cx.nranks * rec;
+            MOR_TRY(comm_allgather(ta.send, gathered, sizeof(double) * (size_t)rec));
+            deim_tail_global_kernel<<<1, DEIM_THREADS, 0, cx.stream>>>(ta, gathered);
+            count_launch();
         }
-        t_tail.stop();
-    }
-    if (blocked) {
-        MOR_CUDA(cudaEventRecord(ev_side, side));
-        MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev_side, 0));
+        if (!blocked) {
+            deim_update_kernel<<<1, 1024, 0, cx.stream>>>(W, Uf, Lm, Z, Zt, c, i, (int)k, ta.last, status_d);
+            count_launch();
+        } else if (j == bw - 1 && l0 + bw < (int)k) {
+            // the panel is complete: extend A = inv(P'U) by its bw rows / columns (block-inverse formula)
+            t_upd.start();
+            deim_sinv_kernel<<<1, DEIM_BLOCK * DEIM_BLOCK, 0, cx.stream>>>(bst, bw, (int)k, l0, Sinv, A);
+            if (l0 > 0) {
+                deim_inv_f_kernel<<<(l0 + 63) / 64, 64, 0, cx.stream>>>(A, W, (int)k, l0, bw, Sinv, Fm);
+                deim_inv_update_kernel<<<dim3((l0 + bw + 15) / 16, (l0 + 15) / 16), 256, 0, cx.stream>>>(A, (int)k, l0, bw, C12,
+                                                                                                   Fm, Sinv);
+                count_launch(2);
+            }
+            count_launch();
+            t_upd.stop();
+        }
     }
     t_total.stop();
+    cx.deim_seq += (unsigned long long)k;
     MOR_CUDA(cudaGetLastError());
     std::vector<long long> idx_h((size_t)k);
+    cx.deim_margins.assign((size_t)k, 0.0);
+    cx.deim_values.assign((size_t)k, 0.0);
     int status_h = 0;
+    unsigned long long tail_ns = 0;
     MOR_CUDA(cudaMemcpyAsync(idx_h.data(), idx_d, sizeof(long long) * (size_t)k, cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(cx.deim_margins.data(), margins_d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(cx.deim_values.data(), values_d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, cx.stream));
     MOR_CUDA(cudaMemcpyAsync(&status_h, status_d, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+    MOR_CUDA(cudaMemcpyAsync(&tail_ns, tail_ns_d, sizeof(tail_ns), cudaMemcpyDeviceToHost, cx.stream));
     MOR_CUDA(cudaStreamSynchronize(cx.stream));
     t_total.collect();
-    t_step.collect();
-    t_tail.collect();
     t_panel.collect();
-    if (ev_rec) cudaEventDestroy(ev_rec);
-    if (ev_side) cudaEventDestroy(ev_side);
+    t_upd.collect();
+    cx.timings[MOR_T_DEIM_TAIL] = (double)tail_ns * 1e-6;
+    cx.timings[MOR_T_DEIM_STEP] = cx.timings[MOR_T_TOTAL] - cx.timings[MOR_T_DEIM_PANEL] - cx.timings[MOR_T_DEIM_UPDATE];
     cx.timings[MOR_T_DEIM_BLOCKED] = blocked ? 1.0 : 0.0;
+    cx.timings[MOR_T_DEIM_EXCHANGE] = cx.nranks == 1 ? 0.0 : (fused ? 1.0 : 2.0);
     for (int64_t i = 0; i < k; ++i) idx_host[i] = (int64_t)idx_h[(size_t)i];
+    if (status_h < 0) {
+        set_error("deim_interpolation_indices: the peer exchange timed out (a rank of the job did not reach the same greedy step)");
+        return MOR_ERR_CUDA;
+    }
     if (status_h != 0) {
         set_error("deim_interpolation_indices: P'U is exactly singular at step " + std::to_string(status_h + 1) +
                   " (SingularException in the reference)");
         return MOR_ERR_SINGULAR;
+    }
+    return MOR_OK;
+}
+
+int32_t deim_indices_device(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host,
+                            const cudaEvent_t* col_ready, int group_cols) {
+    Ctx& cx = ctx();
+    MOR_ARG(B != nullptr && idx_host != nullptr, "deim_interpolation_indices: null pointer");
+    MOR_ARG(k >= 1 && k <= DEIM_MAXK, "deim_interpolation_indices: number of basis columns must be in 1..1024");
+    MOR_ARG(m >= 0 && ld >= (m > 0 ? m : 1), "deim_interpolation_indices: bad m / ld");
+    MOR_TRY(deim_run(B, m, k, ld, idx_host, col_ready, group_cols, true));
+    cx.timings[MOR_T_DEIM_FALLBACK] = 0.0;
+    // Near-tie guard: step 1 is the argmax of |u_1| itself (no arithmetic, the same in every formulation); from
+    // step 2 on, a decision of the blocked path closer than the tolerance is re-made in the reference's formulation.
+    const double tol = deim_tie_tol(k);
+    if (cx.timings[MOR_T_DEIM_BLOCKED] != 0.0 && tol >= 0.0) {
+        double mn = 2.0;
+        for (size_t i = 1; i < cx.deim_margins.size(); ++i) mn = cx.deim_margins[i] < mn ? cx.deim_margins[i] : mn;
+        if (mn < tol) {
+            const double first_ms = cx.timings[MOR_T_TOTAL];
+            if (col_ready != nullptr)   // the whole basis must have landed before the streaming path starts
+                for (int g = 0; g * group_cols < (int)k; ++g) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[g], 0));
+            MOR_TRY(deim_run(B, m, k, ld, idx_host, nullptr, group_cols, false));
+            cx.timings[MOR_T_TOTAL] += first_ms;
+            cx.timings[MOR_T_DEIM_FALLBACK] = 1.0;
+        }
     }
     return MOR_OK;
 }
@@ -800,6 +1123,28 @@ int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t 
     mor_b200_mat_free(dV);
     mor_b200_mat_free(dP);
     return st;
+}
+
+int32_t mor_b200_deim_last_margins(double* margins, double* values, int64_t cap, int64_t* count, double* min_margin,
+                                   int64_t* min_step) {
+    MOR_API_LOCK;
+    const std::vector<double>& mg = ctx().deim_margins;
+    const std::vector<double>& vl = ctx().deim_values;
+    if (count) *count = (int64_t)mg.size();
+    for (int64_t i = 0; i < cap && i < (int64_t)mg.size(); ++i) {
+        if (margins) margins[i] = mg[(size_t)i];
+        if (values) values[i] = vl[(size_t)i];
+    }
+    double mn = 1.0;
+    int64_t at = 0;
+    for (size_t i = 1; i < mg.size(); ++i)
+        if (at == 0 || mg[i] < mn) {
+            mn = mg[i];
+            at = (int64_t)i + 1;
+        }
+    if (min_margin) *min_margin = mn;
+    if (min_step) *min_step = at;
+    return MOR_OK;
 }
 
 int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {

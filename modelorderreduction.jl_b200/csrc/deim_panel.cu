@@ -165,12 +165,9 @@ template <int RT, int KC, int NS>
 int32_t launch_panel(const double* U, int64_t ld, int l0, int bw, const double* Cp, int64_t m, double* R, int64_t ldr) {
     using Cfg = PanelCfg<RT, KC, NS>;
     Ctx& cx = ctx();
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel<RT, KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    // per device (a process may drive several GPUs), so not cached in a static: ~1 us of host time
+    MOR_CUDA(cudaFuncSetAttribute(deim_panel_kernel<RT, KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM));
     const int64_t tiles = (m + RT - 1) / RT;
     const int grid = (int)(tiles < (int64_t)cx.num_sms ? tiles : (int64_t)cx.num_sms);
     deim_panel_kernel<RT, KC, NS><<<grid, PN_THREADS, Cfg::SMEM, cx.stream>>>(U, ld, l0, bw, Cp, m, R, ldr);

@@ -170,11 +170,8 @@ int32_t gemm_nn(const double* X, int64_t ldx, int n, const double* W, int ldw, i
     MOR_TRY(scratch(sizeof(double) * (size_t)nJ * nchunks * NN_WSLAB, reinterpret_cast<void**>(&Wp)));
     pack_w_kernel<<<(unsigned)(nJ * nchunks), 256, 0, cx.stream>>>(W, ldw, n, q, nchunks, upper, Wp);
     MOR_CUDA(cudaGetLastError());
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
-        attr_set = true;
-    }
+    // per device (a process may drive several GPUs), so not cached in a static: ~1 us of host time
+    MOR_CUDA(cudaFuncSetAttribute(gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     const int64_t tiles = (m + NN_RT - 1) / NN_RT;
     MOR_ARG(tiles < (int64_t(1) << 31), "gemm_nn: too many row tiles");
     gemm_nn_kernel<<<(unsigned)tiles, NN_THREADS, NN_SMEM, cx.stream>>>(X, ldx, n, Wp, nchunks, q, m, Y, ldy, upper);

@@ -252,11 +252,8 @@ int32_t launch_tn(const double* A, int64_t lda, int p, const double* B, int64_t 
     MOR_TRY(scratch(sizeof(double) * (size_t)ngroups * ntiles * BM * BN, reinterpret_cast<void**>(&part)));
 
     auto kern = gemm_tn_kernel<BM, BN, WM, WN, KB, STAGES, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    // per device (a process may drive several GPUs), so not cached in a static: ~1 us of host time
+    MOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kern<<<(unsigned)(ngroups * ntiles), Cfg::THREADS, Cfg::SMEM, cx.stream>>>(mapA, mapB, same ? 1 : 0, tiles_q,
                                                                                  ntiles, (int)ngroups, npanels, part);
     MOR_CUDA(cudaGetLastError());

@@ -410,11 +410,8 @@ int32_t gemm_tn_streamk(const double* A, int64_t lda, int p, const double* B, in
     MOR_CUDA(cudaMemcpyAsync(d_cta, cta_seg.data(), sizeof(int) * cta_seg.size(), cudaMemcpyHostToDevice, cx.stream));
     MOR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, cx.stream));
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOR_CUDA(cudaFuncSetAttribute(gemm_tn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
-        attr_set = true;
-    }
+    // per device (a process may drive several GPUs), so not cached in a static: ~1 us of host time
+    MOR_CUDA(cudaFuncSetAttribute(gemm_tn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
     static const bool want_tlog = getenv("MOR_B200_SK_TLOG") != nullptr;
     DevBuf tlog;
     if (want_tlog) MOR_TRY(tlog.alloc(sizeof(unsigned long long) * 3 * (size_t)nct));

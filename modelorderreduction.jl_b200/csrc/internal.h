@@ -50,7 +50,26 @@ struct Ctx {
     size_t scratch_bytes = 0;
     void* ingest_p = nullptr;           // parked device copy of the last large host-ingested matrix:
     size_t ingest_bytes = 0;            // cudaMalloc/cudaFree of 137 GB cost ~0.4 s per call otherwise
+    // DEIM exchange mailbox (deim.cu, nccl.cpp): per greedy step every rank stores its candidate record into every
+    // peer's mailbox over NVLink and raises a flag there -- no NCCL call on the 256-step latency chain
+    void* box_base = nullptr;           // one cudaMalloc: flags | ticket | records
+    double* box = nullptr;
+    unsigned long long* box_flags = nullptr;
+    unsigned* box_ticket = nullptr;
+    void* peer_base[8] = {nullptr};     // peers' mailboxes mapped into this process (CUDA IPC) or this device (P2P)
+    double* peer_box[8] = {nullptr};
+    unsigned long long* peer_flags[8] = {nullptr};
+    bool peers_tried = false, peers_ok = false, peers_ipc = false;
+    unsigned long long deim_seq = 0;    // greedy steps taken since comm_init (the same on every rank): slot / flag value
+    std::vector<double> deim_margins;   // relative gap to the runner-up at every greedy step of the last call
+    std::vector<double> deim_values;    // the winning residual of every greedy step of the last call
 };
+// mailbox geometry (shared by deim.cu and nccl.cpp)
+constexpr int MBOX_SLOTS = 4, MBOX_MAXRANKS = 8, MBOX_REC_MAX = 1024 + 16 + 4 + 3;
+constexpr size_t MBOX_HEADER_BYTES = 1024;   // flags (SLOTS x MAXRANKS u64) then the ticket at byte 512
+constexpr size_t MBOX_BYTES = MBOX_HEADER_BYTES + sizeof(double) * (size_t)(MBOX_SLOTS * MBOX_MAXRANKS + 1) * MBOX_REC_MAX;
+int32_t deim_mailbox();   // allocate the own mailbox; with several ranks, map the peers' (all ranks or none)
+void deim_mailbox_release();
 Ctx& ctx();
 int32_t require_ctx();
 // Every public entry point holds this (recursive: entry points call each other) for its duration:

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "internal.h"
 
@@ -112,6 +113,96 @@ int32_t comm_allgather_i64(int64_t mine, std::vector<int64_t>& all) {
     return MOR_OK;
 }
 
+// ---- DEIM mailbox: the per-step candidate exchange goes over peer memory, not through NCCL ------------------------
+static void mailbox_set_pointers(Ctx& c) {
+    unsigned char* b = static_cast<unsigned char*>(c.box_base);
+    c.box_flags = reinterpret_cast<unsigned long long*>(b);
+    c.box_ticket = reinterpret_cast<unsigned*>(b + 512);
+    c.box = reinterpret_cast<double*>(b + MBOX_HEADER_BYTES);
+    c.peer_base[c.rank] = c.box_base;
+    c.peer_box[c.rank] = c.box;
+    c.peer_flags[c.rank] = c.box_flags;
+}
+
+void deim_mailbox_release() {
+    Ctx& c = ctx();
+    for (int r = 0; r < MBOX_MAXRANKS; ++r) {
+        if (c.peers_ipc && c.peer_base[r] && c.peer_base[r] != c.box_base) cudaIpcCloseMemHandle(c.peer_base[r]);
+        c.peer_base[r] = nullptr;
+        c.peer_box[r] = nullptr;
+        c.peer_flags[r] = nullptr;
+    }
+    if (c.box_base) cudaFree(c.box_base);
+    c.box_base = nullptr;
+    c.box = nullptr;
+    c.box_flags = nullptr;
+    c.box_ticket = nullptr;
+    c.peers_tried = c.peers_ok = c.peers_ipc = false;
+    c.deim_seq = 0;
+    cudaGetLastError();
+}
+
+int32_t deim_mailbox() {
+    Ctx& c = ctx();
+    if (!c.box_base) {
+        MOR_CUDA(cudaMalloc(&c.box_base, MBOX_BYTES));
+        MOR_CUDA(cudaMemset(c.box_base, 0, MBOX_BYTES));
+        MOR_CUDA(cudaDeviceSynchronize());      // zeroed before any peer can learn the address
+        mailbox_set_pointers(c);
+    }
+    if (c.nranks <= 1 || c.peers_tried) return MOR_OK;
+    c.peers_tried = true;
+    // One process per GPU: export the mailbox with CUDA IPC, all-gather the handles (the one NCCL call of the setup),
+    // map every peer's mailbox.  All ranks or none: otherwise the exchange stays on ncclAllGather.
+    const char* ex = getenv("MOR_B200_DEIM_EXCHANGE");
+    bool ok = !(ex && strcmp(ex, "nccl") == 0);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine, c.box_base) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+    }
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> all((size_t)c.nranks);
+    {
+        DevBuf d;
+        MOR_TRY(d.alloc(hb * (size_t)(c.nranks + 1)));
+        unsigned char* dp = d.as<unsigned char>();
+        MOR_CUDA(cudaMemcpyAsync(dp + hb * (size_t)c.nranks, &mine, hb, cudaMemcpyHostToDevice, c.stream));
+        MOR_TRY(comm_allgather(dp + hb * (size_t)c.nranks, dp, hb));
+        MOR_CUDA(cudaMemcpyAsync(all.data(), dp, hb * (size_t)c.nranks, cudaMemcpyDeviceToHost, c.stream));
+        MOR_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    void* mapped[MBOX_MAXRANKS] = {nullptr};
+    for (int r = 0; r < c.nranks && ok; ++r) {
+        if (r == c.rank) continue;
+        if (cudaIpcOpenMemHandle(&mapped[r], all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            mapped[r] = nullptr;
+            ok = false;
+        }
+    }
+    std::vector<int64_t> votes;
+    MOR_TRY(comm_allgather_i64(ok ? 1 : 0, votes));
+    for (int64_t v : votes) ok = ok && v != 0;
+    if (!ok) {
+        for (int r = 0; r < c.nranks; ++r)
+            if (mapped[r]) cudaIpcCloseMemHandle(mapped[r]);
+        cudaGetLastError();
+        return MOR_OK;
+    }
+    for (int r = 0; r < c.nranks; ++r) {
+        if (r == c.rank) continue;
+        unsigned char* b = static_cast<unsigned char*>(mapped[r]);
+        c.peer_base[r] = mapped[r];
+        c.peer_flags[r] = reinterpret_cast<unsigned long long*>(b);
+        c.peer_box[r] = reinterpret_cast<double*>(b + MBOX_HEADER_BYTES);
+    }
+    c.peers_ipc = true;
+    c.peers_ok = true;
+    return MOR_OK;
+}
+
 }  // namespace mor
 
 using namespace mor;
@@ -135,6 +226,7 @@ int32_t mor_b200_comm_init(int32_t rank, int32_t nranks, const void* id128) {
     MOR_TRY(require_ctx());
     Ctx& c = ctx();
     if (c.comm) mor_b200_comm_destroy();
+    deim_mailbox_release();   // flags / step counter restart with the communicator
     if (nranks == 1) {
         c.rank = 0;
         c.nranks = 1;
@@ -169,6 +261,8 @@ int32_t mor_b200_comm_destroy(void) {
         }
         g_nccl.CommDestroy((ncclComm_t)c.comm);
     }
+    if (c.ready) cudaSetDevice(c.device);
+    deim_mailbox_release();
     c.comm = nullptr;
     c.rank = 0;
     c.nranks = 1;

@@ -16,7 +16,7 @@ MOR_SVD, MOR_TSVD, MOR_RSVD = 0, 1, 2
 SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK, SYNTH_KAT, SYNTH_BURGERS = 0, 1, 2, 3, 4
 POD_MAY_OVERWRITE, POD_FORCE_TWO_PASS = 1, 2
 T_SLOTS = ("total", "h2d", "gram", "apply", "core", "basis", "comm", "deim_step", "deim_tail",
-           "d2h", "sketch", "deim_panel", "deim_blocked")
+           "d2h", "sketch", "deim_panel", "deim_blocked", "deim_update", "deim_fallback", "deim_exchange")
 T_NSLOTS = 16
 
 
@@ -60,6 +60,7 @@ SIGNATURES = {
     "mor_b200_pod_free": (_i32, [_p]),
     "mor_b200_pod_info": (_i32, [_p, _pi32, _pi32]),
     "mor_b200_deim_indices": (_i32, [_p, _i64, _i64, _i64, _p]),
+    "mor_b200_deim_last_margins": (_i32, [_pd, _pd, _i64, _pi64, _pd, _pi64]),
     "mor_b200_deim_projector": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _p, _i64]),
     "mor_b200_deim_projector_dev": (_i32, [_p, _p, _p, _p]),
     "mor_b200_galerkin_csc": (_i32, [_i64, _p, _p, _p, _p, _i64, _i64, _p, _i64]),

@@ -23,6 +23,28 @@ def deim_interpolation_indices(basis: np.ndarray) -> np.ndarray:
     return idx
 
 
+def deim_last_margins(with_values: bool = False):
+    """(margins, min_margin, min_step) of the last `deim_interpolation_indices` call: margins[l] is the relative gap
+    between the best and the second-best residual at greedy step l+1 (mor_b200_deim_last_margins); the minimum is
+    over steps >= 2.  `with_values`: also the winning residuals.  Not in the reference: it tells a caller how far
+    above FP64 rounding each choice was."""
+    import ctypes as C
+    lib = _lib.load()
+    n = C.c_int64(0)
+    _lib.check(lib.mor_b200_deim_last_margins(None, None, 0, C.byref(n), None, None))
+    m, v = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    mn, at = C.c_double(1.0), C.c_int64(0)
+    pd = C.POINTER(C.c_double)
+    _lib.check(lib.mor_b200_deim_last_margins(m.ctypes.data_as(pd), v.ctypes.data_as(pd), n.value, None, C.byref(mn), C.byref(at)))
+    if with_values:
+        return m[:n.value], mn.value, at.value, v[:n.value]
+    return m[:n.value], mn.value, at.value
+
+
+def deim_last_margin() -> float:
+    return deim_last_margins()[1]
+
+
 def deim_projector(U: np.ndarray, V: np.ndarray, indices: np.ndarray) -> np.ndarray:
     """`((@view U[indices, :])' \\ (U' * V))'` -- the DEIM projector assembled inside the numeric
     `deim(...)` at /root/reference/src/deim.jl:150, rerouted to mor_b200_deim_projector.  U is the

@@ -39,6 +39,9 @@ for stage in "$@"; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$NG" --master-addr 127.0.0.1 --master-port 29617 \
         tests/multi_gpu_check.py > gpurun_out/multi_check_n$NG.txt 2>&1
       echo "multi_gpu_check exit $?" >> gpurun_out/multi_check_n$NG.txt; tail -n 6 gpurun_out/multi_check_n$NG.txt
+      MOR_B200_DEIM_EXCHANGE=nccl timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$NG" --master-addr 127.0.0.1 \
+        --master-port 29619 tests/multi_gpu_check.py > gpurun_out/multi_check_nccl_n$NG.txt 2>&1
+      echo "multi_gpu_check (NCCL exchange) exit $?" >> gpurun_out/multi_check_nccl_n$NG.txt; tail -n 3 gpurun_out/multi_check_nccl_n$NG.txt
       timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$NG" --master-addr 127.0.0.1 --master-port 29618 \
         bench.py --gpus "$NG" --steps 3 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
       echo "bench N=$NG exit $?" >> gpurun_out/bench_n$NG.err; tail -n 3 gpurun_out/bench_n$NG.err; cat gpurun_out/bench_n$NG.json ;;

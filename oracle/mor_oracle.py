@@ -353,6 +353,32 @@ class _BorderedLU:
         return np.triu(self.Z[:l, :l]) @ self.Uf[:l, cols]
 
 
+class _BlockInverse:
+    """A = inv(P'U) kept explicitly the way the library keeps it on the blocked path (csrc/deim.cu: deim_coef_kernel,
+    deim_sinv_kernel, deim_inv_f_kernel, deim_inv_update_kernel): W holds the rows of the basis at the chosen
+    points; once per panel A grows by the block-inverse formula with the panel's own LU factors S = L Uf,
+        M = [W11 W12; W21 W22],  C12 = A W12,  S = W22 - W21 C12,  F = inv(S) (W21 A),
+        inv(M) = [A + C12 F, -C12 inv(S); -F, inv(S)]."""
+
+    def __init__(self, k: int):
+        self.k = k
+        self.A, self.W = np.zeros((k, k)), np.zeros((k, k))
+
+    def coefficients(self, l0: int, W12: Array) -> Array:
+        return self.A[:l0, :l0] @ W12
+
+    def extend(self, l0: int, bw: int, C12: Optional[Array], S1: "_BorderedLU") -> None:
+        Lfull = np.tril(S1.L[:bw, :bw], -1) + np.eye(bw)
+        Sinv = np.triu(S1.Z[:bw, :bw]) @ sla.solve_triangular(Lfull, np.eye(bw), lower=True, unit_diagonal=True)
+        A = self.A
+        if l0 > 0:
+            F = Sinv @ (self.W[l0:l0 + bw, :l0] @ A[:l0, :l0])
+            A[:l0, :l0] += C12 @ F
+            A[:l0, l0:l0 + bw] = -C12 @ Sinv
+            A[l0:l0 + bw, :l0] = -F
+        A[l0:l0 + bw, l0:l0 + bw] = Sinv
+
+
 def deim_interpolation_indices_blocked(basis: Array, block: int = 16, sub: int = 4) -> Array:
     """The library's blocked DEIM (csrc/deim.cu, csrc/deim_panel.cu) restated in numpy: the residual
     r_l = u_l - U_{l-1} inv(P'U_{l-1}) P'u_l of deim.jl:21-23 is column l of the Schur complement of an
@@ -362,11 +388,12 @@ def deim_interpolation_indices_blocked(basis: Array, block: int = 16, sub: int =
     sub-panel.  Same indices as :func:`deim_interpolation_indices` (tests/test_oracle.py)."""
     U = np.asarray(basis, dtype=np.float64)
     m, k = U.shape
-    G = _BorderedLU(k)
+    G = _BlockInverse(k)
     idx = []
     for l0 in range(0, k, block):
         bw = min(block, k - l0)
-        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ G.coefficients(l0, slice(l0, l0 + bw))
+        C12 = G.coefficients(l0, G.W[:l0, l0:l0 + bw]) if l0 else None
+        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ C12
         S1 = _BorderedLU(bw)
         for s0 in range(0, bw, sub):
             sw = min(sub, bw - s0)
@@ -376,23 +403,25 @@ def deim_interpolation_indices_blocked(basis: Array, block: int = 16, sub: int =
                 r = np.abs(P2[:, jj] - P2[:, :jj] @ S2.c[:jj]) if jj else np.abs(P2[:, 0])
                 p = argmax_first(r)
                 idx.append(p)
-                G.append(l0 + s0 + jj, U[p, :].copy())
+                G.W[l0 + s0 + jj, :] = U[p, :]
                 S1.append(s0 + jj, P1[p, :].copy())
                 S2.append(jj, P2[p, :].copy())
+        if l0 + bw < k:
+            G.extend(l0, bw, C12, S1)
     return np.array(idx, dtype=np.int64) + 1
 
 
 def deim_interpolation_indices_blocked_sharded(local_basis: Array, row_offset: int, allgather, allreduce_sum,
                                                block: int = 16, sub: int = 4, cols_ready=None) -> Array:
     """The blocked DEIM over contiguous row shards, with the library's exchange steps: per greedy step one
-    all-gather of (value, global index, rows of the basis / panel / sub-panel at that index); with pipelined
-    ingest (``cols_ready(l)`` = number of basis columns that have landed when step l starts) the rows of the
-    chosen points are only gathered up to the current panel, and the later columns are caught up at each panel
-    boundary by gathering them from their owners (zeros elsewhere) and all-reducing -- csrc/deim.cu:
-    deim_gather_block_kernel / deim_fwd_subst_kernel.  Panels and sub-panels are local to each rank."""
+    exchange of (value, global index, rows of the basis / panel / sub-panel at that index) between all ranks (peer
+    mailboxes over NVLink in the library, `allgather` here); with pipelined ingest (``cols_ready(l)`` = number of
+    basis columns that have landed when step l starts) the rows of the chosen points are only known up to the
+    current panel, and the later columns are fetched at each panel boundary from their owners (zeros elsewhere,
+    all-reduced) -- csrc/deim.cu: deim_gather_block_kernel.  Panels and sub-panels are local to each rank."""
     U = np.asarray(local_basis, dtype=np.float64)
     m, k = U.shape
-    G = _BorderedLU(k)
+    G = _BlockInverse(k)
     idx = []
     defer = cols_ready is not None
 
@@ -405,13 +434,15 @@ def deim_interpolation_indices_blocked_sharded(local_basis: Array, row_offset: i
 
     for l0 in range(0, k, block):
         bw = min(block, k - l0)
-        if defer:
-            assert cols_ready(l0) >= l0 + bw, "a panel needs the columns up to its own"
-            if l0 > 0:                                   # catch up the deferred columns of the U-factor
+        C12 = None
+        if l0 > 0:
+            if defer:
+                assert cols_ready(l0) >= l0 + bw, "a panel needs the columns up to its own"
                 W12 = owned_rows(slice(l0, l0 + bw))
-                Lfull = np.tril(G.L[:l0, :l0], -1) + np.eye(l0)
-                G.Uf[:l0, l0:l0 + bw] = sla.solve_triangular(Lfull, W12, lower=True, unit_diagonal=True)
-        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ G.coefficients(l0, slice(l0, l0 + bw))
+            else:
+                W12 = G.W[:l0, l0:l0 + bw]
+            C12 = G.coefficients(l0, W12)
+        P1 = U[:, l0:l0 + bw] if l0 == 0 else U[:, l0:l0 + bw] - U[:, :l0] @ C12
         S1 = _BorderedLU(bw)
         for s0 in range(0, bw, sub):
             sw = min(sub, bw - s0)
@@ -432,22 +463,11 @@ def deim_interpolation_indices_blocked_sharded(local_basis: Array, row_offset: i
                     if c[1] >= 0 and (best is None or _better(c[0], c[1], best[0], best[1])):
                         best = c
                 idx.append(best[1])
-                i = l0 + s0 + jj
-                if defer:                                # bordered update confined to the panel's columns
-                    w = best[2]
-                    ell = np.array([w[:j + 1] @ G.Z[:j + 1, j] for j in range(i)])
-                    G.L[i, :i] = ell
-                    G.Uf[i, i:l0 + bw] = w[i:l0 + bw] - ell @ G.Uf[:i, i:l0 + bw]
-                    piv = G.Uf[i, i]
-                    if piv == 0.0 and i < k - 1:
-                        raise np.linalg.LinAlgError("SingularException")
-                    for rr in range(i):
-                        G.Z[rr, i] = -(G.Z[rr, rr:i] @ G.Uf[rr:i, i]) / piv
-                    G.Z[i, i] = 1.0 / piv
-                else:
-                    G.append(i, best[2])
+                G.W[l0 + s0 + jj, :] = best[2]
                 S1.append(s0 + jj, best[3])
                 S2.append(jj, best[4])
+        if l0 + bw < k:
+            G.extend(l0, bw, C12, S1)
     return np.array(idx, dtype=np.int64) + 1
 
 

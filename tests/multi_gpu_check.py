@@ -99,8 +99,28 @@ def main():
     T = np.zeros((100_000, 2)); T[:, 0] = 1.0; T[70_000, 0] = -4.0; T[20_000, 0] = 4.0; T[:, 1] = np.arange(100_000) % 5
     row0, m_loc = mdist.shard_rows(T.shape[0], world, rank)
     assert deim_indices_dev(DeviceMatrix.from_host(T[row0:row0 + m_loc])).tolist() == O.deim_interpolation_indices(T).tolist()
+    # k = 256 (the headline dimension) sharded: blocked and streaming paths, both against the oracle
+    Q, _ = np.linalg.qr(rng.standard_normal((131_072, 256)))
+    row0, m_loc = mdist.shard_rows(Q.shape[0], world, rank)
+    dQ = DeviceMatrix.from_host(Q[row0:row0 + m_loc])
+    want, margins = O.deim_interpolation_indices(Q, return_margins=True)
+    got = deim_indices_dev(dQ)
+    t = _lib.last_timings()
+    assert got.tolist() == want.tolist(), "k=256 blocked path differs from the oracle"
+    assert t["deim_blocked"] == 1.0 or t["deim_fallback"] == 1.0
+    want_exchange = 2.0 if os.environ.get("MOR_B200_DEIM_EXCHANGE") == "nccl" else 1.0
+    assert t["deim_exchange"] == want_exchange, f"per-step exchange mode {t['deim_exchange']} (1 = peer mailboxes, 2 = NCCL)"
+    import mor_b200
+    mg = mor_b200.deim_last_margins()[0]
+    if t["deim_fallback"] == 0.0:
+        np.testing.assert_allclose(mg[1:], margins[1:], rtol=1e-6, atol=1e-9)
+    os.environ["MOR_B200_DEIM_BLOCK"] = "0"
+    got_s = deim_indices_dev(dQ)
+    del os.environ["MOR_B200_DEIM_BLOCK"]
+    assert got_s.tolist() == want.tolist(), "k=256 streaming path differs from the oracle"
     if rank == 0:
-        print(f"DEIM ok on {world} GPUs", flush=True)
+        print(f"DEIM ok on {world} GPUs (k=256 blocked + streaming vs oracle; per-step exchange: "
+              f"{'peer mailboxes over NVLink' if want_exchange == 1.0 else 'ncclAllGather'})", flush=True)
 
     # ---- BASELINE config 5 at oracle size: Burgers snapshots generated shard by shard, POD basis, DEIM ----
     nx, n = 192, 48
@@ -113,7 +133,7 @@ def main():
     assert O.sigma_error(np.linalg.svd(S_all, compute_uv=False), f.s) <= 1e-10
     Ub = f.basis(n, DeviceMatrix.alloc(m_loc, n))
     idx = deim_indices_dev(Ub)
-    assert _lib.last_timings()["deim_blocked"] == 1.0
+    assert _lib.last_timings()["deim_blocked"] == 1.0 or _lib.last_timings()["deim_fallback"] == 1.0
     assert idx.tolist() == O.deim_interpolation_indices(gather_rows(Ub.to_host())).tolist()
     if rank == 0:
         print(f"Burgers config 5 (sharded generator, POD basis, blocked DEIM) ok on {world} GPUs", flush=True)

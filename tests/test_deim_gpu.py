@@ -265,8 +265,14 @@ def test_headline_k256_vs_oracle(gpu, monkeypatch, kind):
     want, margins = O.deim_interpolation_indices(Bh, return_margins=True)
     want = want.tolist()
     got = deim_indices_dev(B).tolist()
-    assert _lib.last_timings()["deim_blocked"] == 1.0
+    t = _lib.last_timings()
+    assert t["deim_blocked"] == 1.0 or t["deim_fallback"] == 1.0
     assert got == want, "blocked: " + _first_difference_report(got, want, margins)
+    # the library's own margins (from the blocked path's residuals) against the oracle's
+    mg, mn, at = mor_b200.deim_last_margins()
+    assert mg.shape == (k,) and 0.0 <= mn <= 1.0 and 2 <= at <= k
+    if t["deim_fallback"] == 0.0:
+        np.testing.assert_allclose(mg[1:], margins[1:], rtol=1e-6, atol=1e-9)
     got = mor_b200.deim_interpolation_indices(Bh).tolist()          # host pointers: pipelined ingest
     assert got == want, "host entry: " + _first_difference_report(got, want, margins)
     monkeypatch.setenv("MOR_B200_DEIM_BLOCK", "0")
@@ -274,3 +280,41 @@ def test_headline_k256_vs_oracle(gpu, monkeypatch, kind):
     assert _lib.last_timings()["deim_blocked"] == 0.0
     assert got == want, "streaming: " + _first_difference_report(got, want, margins)
     assert len(set(want)) == k
+
+
+def test_margins_and_tie_fallback(gpu, monkeypatch):
+    """mor_b200_deim_last_margins: the relative gap to the runner-up at every greedy step; a near-tie at a step >= 2 of
+    the blocked path repeats the call in the reference's formulation (streaming path)."""
+    monkeypatch.delenv("MOR_B200_DEIM_BLOCK", raising=False)
+    monkeypatch.delenv("MOR_B200_DEIM_TIE_FALLBACK", raising=False)
+    rng = np.random.Generator(np.random.PCG64(9))
+    m, k = 40_000, 40
+    Q = np.asfortranarray(np.linalg.qr(rng.standard_normal((m, k)))[0])
+    want, margins = O.deim_interpolation_indices(Q, return_margins=True)
+    assert mor_b200.deim_interpolation_indices(Q).tolist() == want.tolist()
+    t = _lib.last_timings()
+    assert t["deim_blocked"] == 1.0 and t["deim_fallback"] == 0.0
+    mg, mn, at = mor_b200.deim_last_margins()
+    np.testing.assert_allclose(mg, margins, rtol=1e-7, atol=1e-10)
+    assert mn == pytest.approx(margins[1:].min(), rel=1e-7) and at == int(np.argmin(margins[1:])) + 2
+    mg2, _, _, vals = mor_b200.deim_last_margins(with_values=True)
+    assert np.array_equal(mg2, mg) and vals.shape == (k,) and np.all(vals > 0)
+    assert vals[0] == np.abs(Q[:, 0]).max()
+    # duplicated rows: every step is an exact tie (margin 0) -> fallback to the streaming path, same indices
+    A = rng.standard_normal((m, k))
+    A[30_000:] = A[:10_000]
+    A = np.asfortranarray(A)
+    idx = mor_b200.deim_interpolation_indices(A)
+    t = _lib.last_timings()
+    assert t["deim_fallback"] == 1.0 and t["deim_blocked"] == 0.0
+    assert idx.tolist() == O.deim_interpolation_indices(A).tolist()
+    assert mor_b200.deim_last_margins()[1] == 0.0
+    monkeypatch.setenv("MOR_B200_DEIM_TIE_FALLBACK", "0")
+    idx2 = mor_b200.deim_interpolation_indices(A)
+    t = _lib.last_timings()
+    assert t["deim_fallback"] == 0.0 and t["deim_blocked"] == 1.0
+    assert idx2.tolist() == idx.tolist()                # exact ties resolve to the lowest index on both paths
+    # streaming path reports margins too
+    monkeypatch.setenv("MOR_B200_DEIM_BLOCK", "0")
+    mor_b200.deim_interpolation_indices(Q)
+    np.testing.assert_allclose(mor_b200.deim_last_margins()[0], margins, rtol=1e-7, atol=1e-10)
