@@ -14,9 +14,14 @@
  *   - plain C, no C++/torch types; every call returns an int32 status (0 = OK).
  *   - matrices are column-major FP64 ("each column is a state snapshot", POD.jl:38-39);
  *     ld* is the leading dimension in elements.  Indices are Int64, 1-based on output.
- *   - one process drives one GPU ("rank").  With mor_b200_comm_init() the ranks of a
+ *   - by default one process drives one GPU ("rank").  With mor_b200_comm_init() the ranks of a
  *     job hold contiguous ROW shards of every matrix, rank order = row order; small
- *     (n x n) results are replicated, tall results (U) stay row-sharded.
+ *     (n x n) results are replicated, tall results (U) stay row-sharded.  Alternatively ONE process
+ *     drives all GPUs of the box and the library does the sharding (mor_b200_init_multi).
+ *   - host matrices may be pageable (a Julia Matrix) or page-locked (mor_b200_host_alloc): pageable ones
+ *     travel through a ring of pinned staging buffers filled by a few host threads.
+ *   - a device matrix handed to mor_b200_pod_factor_dev must stay alive and unmodified until the handle
+ *     is freed (the handle borrows it unless a second pass had to copy it).
  *   - host buffers are read/written only during the call; nothing is retained.
  *   - calls are synchronous (they return after the work is done) unless named *_async.
  *   - no CPU fallback exists: without a usable CUDA device every compute entry point
@@ -80,7 +85,17 @@ int32_t mor_b200_trim(void);
 int32_t mor_b200_host_alloc(uint64_t bytes, void** out);
 int32_t mor_b200_host_free(void* p);
 
-/* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------------------- */
+/* ---- multi-GPU, form 1: ONE process drives the whole box ------------------------------------
+ * mor_b200_init_multi(ngpus) (or MOR_B200_NGPUS=ngpus in the environment of a process that never calls
+ * mor_b200_init) starts one worker thread, context, stream set and NCCL rank per GPU.  The host-pointer entry points
+ * below (pod_factor[_cols], pod_basis, deim_indices, deim_projector, project) then take the WHOLE matrix: the library
+ * shards its rows over the GPUs, replicated results (spectrum, indices, projector) come back once and the tall result
+ * is written into the caller's U_out by all GPUs -- reduce!(pod, SVD()) from a single Julia session uses 8 GPUs.
+ * Wide or tiny inputs, mor_b200_galerkin_csc and the device-resident API (mor_b200_mat_*, *_dev) run on GPU 0. */
+int32_t mor_b200_init_multi(int32_t ngpus);
+int32_t mor_b200_multi_info(int32_t* ngpus); /* 0 when the mode is off */
+
+/* ---- multi-GPU, form 2: one process per GPU, NCCL over NVLink ------------------------------- */
 /* Rank 0 creates a 128-byte NCCL unique id; the host runtime (Julia Distributed / MPI,
  * torch.distributed, ...) broadcasts it; every rank then calls comm_init. */
 int32_t mor_b200_comm_unique_id(void* id128);

@@ -10,8 +10,10 @@
 namespace mor {
 
 static thread_local std::string g_last_error;
-static Ctx g_ctx;
+static Ctx g_ctxs[MBOX_MAXRANKS];          // [0]: the process-wide context; [r]: GPU r of the multi-GPU mode
+static thread_local Ctx* tl_ctx = &g_ctxs[0];
 static std::mutex g_mutex;
+#define g_ctx (*tl_ctx)
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -25,7 +27,10 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return e == cudaErrorMemoryAllocation ? MOR_ERR_NOMEM : MOR_ERR_CUDA;
 }
 
-Ctx& ctx() { return g_ctx; }
+Ctx& ctx() { return *tl_ctx; }
+Ctx& ctx_of(int r) { return g_ctxs[r]; }
+void bind_ctx(int r) { tl_ctx = &g_ctxs[r]; }
+const std::string& last_error_string() { return g_last_error; }
 
 std::recursive_mutex& api_mutex() {
     static std::recursive_mutex m;
@@ -198,20 +203,8 @@ void Timer::collect() {
     spans.clear();
 }
 
-}  // namespace mor
-
-using namespace mor;
-
-extern "C" {
-
-int32_t mor_b200_version(void) { return MOR_B200_VERSION; }
-
-const char* mor_b200_last_error(void) { return g_last_error.c_str(); }
-
-int32_t mor_b200_init(int32_t device) {
-    MOR_API_LOCK;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (g_ctx.ready && g_ctx.device == device) return MOR_OK;
+int32_t init_device(Ctx& c, int device) {
+    if (c.ready && c.device == device) return MOR_OK;
     MOR_ARG(device >= 0, "mor_b200_init: device must be >= 0");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -228,9 +221,9 @@ int32_t mor_b200_init(int32_t device) {
         set_error("mor_b200_init: libmor_b200 is built for sm_100a (B200) only");
         return MOR_ERR_CUDA;
     }
-    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
-    MOR_CUDA(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
-    g_ctx.stream = g_ctx.own_stream;
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    MOR_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
     {   // keep up to POOL_KEEP of freed work buffers cached in the default pool
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -239,40 +232,71 @@ int32_t mor_b200_init(int32_t device) {
         }
         cudaGetLastError();
     }
-    g_ctx.device = device;
-    g_ctx.num_sms = prop.multiProcessorCount;
-    g_ctx.ready = true;
+    c.device = device;
+    c.num_sms = prop.multiProcessorCount;
+    c.ready = true;
     return MOR_OK;
+}
+
+// the calling thread must be the one whose ctx() is `c` (DevBuf / mailbox helpers go through ctx())
+void teardown_device(Ctx& c) {
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    if (c.scratch_p) cudaFree(c.scratch_p);
+    c.scratch_p = nullptr;
+    c.scratch_bytes = 0;
+    if (c.ingest_p) cudaFree(c.ingest_p);
+    c.ingest_p = nullptr;
+    c.ingest_bytes = 0;
+    deim_mailbox_release();
+    stage_release();
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    c.copy_stream = nullptr;
+    if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    c.aux_stream = nullptr;
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    c.own_stream = nullptr;
+    c.stream = nullptr;
+    c.ready = false;
+}
+
+}  // namespace mor
+
+using namespace mor;
+
+extern "C" {
+
+int32_t mor_b200_version(void) { return MOR_B200_VERSION; }
+
+const char* mor_b200_last_error(void) { return g_last_error.c_str(); }
+
+int32_t mor_b200_init(int32_t device) {
+    MOR_API_LOCK;
+    if (multi_on() && !is_worker()) {
+        set_error("mor_b200_init: the library is in single-process multi-GPU mode (mor_b200_init_multi); call mor_b200_shutdown first");
+        return MOR_ERR_ARG;
+    }
+    multi_skip_env();            // an explicit single-device init wins over MOR_B200_NGPUS
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return init_device(g_ctx, device);
 }
 
 int32_t mor_b200_shutdown(void) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_shutdown();
     mor_b200_comm_destroy();
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (g_ctx.ready) {
-        cudaSetDevice(g_ctx.device);
-        cudaStreamSynchronize(g_ctx.stream);
-        if (g_ctx.scratch_p) cudaFree(g_ctx.scratch_p);
-        g_ctx.scratch_p = nullptr;
-        g_ctx.scratch_bytes = 0;
-        if (g_ctx.ingest_p) cudaFree(g_ctx.ingest_p);
-        g_ctx.ingest_p = nullptr;
-        g_ctx.ingest_bytes = 0;
-        deim_mailbox_release();
-        if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
-        g_ctx.copy_stream = nullptr;
-        if (g_ctx.aux_stream) cudaStreamDestroy(g_ctx.aux_stream);
-        g_ctx.aux_stream = nullptr;
-        if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
-        g_ctx.own_stream = nullptr;
-        g_ctx.stream = nullptr;
-        g_ctx.ready = false;
-    }
+    teardown_device(g_ctx);
     return MOR_OK;
 }
 
 int32_t mor_b200_set_stream(void* cuda_stream) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) {
+        set_error("mor_b200_set_stream: not available in single-process multi-GPU mode (every GPU runs on its own stream)");
+        return MOR_ERR_ARG;
+    }
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
     g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
@@ -281,6 +305,7 @@ int32_t mor_b200_set_stream(void* cuda_stream) {
 
 int32_t mor_b200_sync(void) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_all([](int) -> int32_t { return mor_b200_sync(); });
     MOR_TRY(require_ctx());
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return MOR_OK;
@@ -288,6 +313,7 @@ int32_t mor_b200_sync(void) {
 
 int32_t mor_b200_trim(void) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_all([](int) -> int32_t { return mor_b200_trim(); });
     MOR_TRY(require_ctx());
     trim_pool();
     return MOR_OK;
@@ -298,7 +324,7 @@ int32_t mor_b200_host_alloc(uint64_t bytes, void** out) {
     MOR_ARG(out != nullptr, "mor_b200_host_alloc: null output pointer");
     MOR_TRY(require_ctx());
     void* p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, bytes > 0 ? (size_t)bytes : 8, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, bytes > 0 ? (size_t)bytes : 8, cudaHostAllocPortable);   // every GPU of the process may DMA from it
     if (e != cudaSuccess) {
         *out = nullptr;
         return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
@@ -320,14 +346,21 @@ int32_t mor_b200_last_timings(double* ms, int32_t n) {
 }
 
 int64_t mor_b200_launch_count(int32_t reset) {
-    int64_t v = g_ctx.launches;
-    if (reset) g_ctx.launches = 0;
+    MOR_API_LOCK;
+    int64_t v = 0;
+    const int n = multi_on() && !is_worker() ? multi_n() : 1;
+    for (int r = 0; r < n; ++r) {
+        Ctx& c = n > 1 ? ctx_of(r) : g_ctx;
+        v += c.launches;
+        if (reset) c.launches = 0;
+    }
     return v;
 }
 
 // ---- device matrices ----------------------------------------------------------------------
 int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_mat_alloc(m, n, out));
     MOR_ARG(out != nullptr && m >= 0 && n >= 0, "mor_b200_mat_alloc: bad arguments");
     MOR_TRY(require_ctx());
     int64_t ld = (m + 1) & ~int64_t(1);  // even: 16-byte aligned columns (TMA / v2 loads)
@@ -356,6 +389,7 @@ int32_t mor_b200_mat_alloc(int64_t m, int64_t n, mor_mat_t* out) {
 
 int32_t mor_b200_mat_wrap(void* device_ptr, int64_t m, int64_t n, int64_t ld, mor_mat_t* out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_mat_wrap(device_ptr, m, n, ld, out));
     MOR_ARG(out != nullptr && device_ptr != nullptr && m >= 0 && n >= 0 && ld >= m && ld >= 1,
             "mor_b200_mat_wrap: bad arguments");
     MOR_TRY(require_ctx());
@@ -371,6 +405,7 @@ int32_t mor_b200_mat_wrap(void* device_ptr, int64_t m, int64_t n, int64_t ld, mo
 
 int32_t mor_b200_mat_free(mor_mat_t a) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_mat_free(a));
     if (!a) return MOR_OK;
     if (a->owned && a->p) {
         if (g_ctx.ready) {
@@ -394,29 +429,29 @@ int32_t mor_b200_mat_info(mor_mat_t a, int64_t* m, int64_t* n, int64_t* ld, void
 
 int32_t mor_b200_mat_upload(mor_mat_t a, const double* host, int64_t ldh) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_mat_upload(a, host, ldh));
     MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_upload: bad arguments");
     MOR_TRY(require_ctx());
     if (a->m == 0 || a->n == 0) return MOR_OK;
-    MOR_CUDA(cudaMemcpy2DAsync(a->p, (size_t)a->ld * 8, host, (size_t)ldh * 8, (size_t)a->m * 8,
-                               (size_t)a->n, cudaMemcpyHostToDevice, g_ctx.stream));
+    MOR_TRY(h2d_2d(a->p, a->ld, host, ldh, a->m, a->n, g_ctx.stream));
     MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return MOR_OK;
 }
 
 int32_t mor_b200_mat_download(mor_mat_t a, double* host, int64_t ldh) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_mat_download(a, host, ldh));
     MOR_ARG(a != nullptr && host != nullptr && ldh >= a->m, "mor_b200_mat_download: bad arguments");
     MOR_TRY(require_ctx());
     if (a->m == 0 || a->n == 0) return MOR_OK;
-    MOR_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, a->p, (size_t)a->ld * 8, (size_t)a->m * 8,
-                               (size_t)a->n, cudaMemcpyDeviceToHost, g_ctx.stream));
-    MOR_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    MOR_TRY(d2h_2d(host, ldh, a->p, a->ld, a->m, a->n, g_ctx.stream));
     return MOR_OK;
 }
 
 int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_row0, double param,
                        int64_t iparam) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_synth(a, kind, seed, global_row0, param, iparam));
     MOR_ARG(a != nullptr && global_row0 >= 0, "mor_b200_synth: bad arguments");
     MOR_TRY(require_ctx());
     MOR_TRY(synth_fill(a->p, a->m, a->n, a->ld, kind, seed, global_row0, param, iparam));
@@ -427,6 +462,7 @@ int32_t mor_b200_synth(mor_mat_t a, int32_t kind, uint64_t seed, int64_t global_
 int32_t mor_b200_kat_check(mor_mat_t U, int64_t k, int64_t n, uint64_t seed, int64_t global_row0, double param,
                            double* max_err) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_kat_check(U, k, n, seed, global_row0, param, max_err));
     MOR_ARG(U != nullptr && max_err != nullptr && k >= 1 && k <= U->n && n >= k && global_row0 >= 0,
             "mor_b200_kat_check: bad arguments");
     MOR_TRY(require_ctx());

@@ -121,14 +121,24 @@ __device__ __forceinline__ void cand_take(double& bv, long long& bi, double& b2,
     }
 }
 
-// ---- system-scope flag traffic of the peer exchange ------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// ---- peer exchange: self-validating 16-byte words (value split in two halves, each next to a 32-bit tag) ----------
+// The same idea as NCCL's LL protocol: a word {lo, tag, hi, tag} needs no fence and no separate flag -- whichever
+// 8-byte half arrives first over NVLink, the reader only accepts it once both tags carry this step's number.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"((unsigned)b), "r"(tag),
+                 "r"((unsigned)(b >> 32)), "r"(tag)
+                 : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ bool ll_load(const uint4* p, unsigned tag, double& v, long long deadline) {
+    unsigned a0, a1, a2, a3;
+    for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "l"(p) : "memory");
+        if (a1 == tag && a3 == tag) break;
+        if (clock64() > deadline) return false;
+    }
+    v = __longlong_as_double((long long)(((unsigned long long)a2 << 32) | a0));
+    return true;
 }
 
 // Everything the fused tail needs (passed by value to the step kernels).
@@ -147,13 +157,11 @@ struct TailArgs {
     int sw;
     int64_t row_offset;
     // exchange
-    double* box;                      // own mailbox: DEIM_SLOTS x nranks records
-    unsigned long long* flags;        // own flags: DEIM_SLOTS x DEIM_MAXRANKS
-    double* peer_box[DEIM_MAXRANKS];  // peers' mailboxes (NVLink peer memory); [rank] = own
-    unsigned long long* peer_flags[DEIM_MAXRANKS];
+    uint4* ll;                        // own mailbox: DEIM_SLOTS x DEIM_MAXRANKS x DEIM_REC_MAX words
+    uint4* peer_ll[DEIM_MAXRANKS];    // the peers' mailboxes (NVLink peer memory)
     double* send;                     // NCCL fallback: the local record goes here instead
     int rank, nranks, rec, slot;
-    unsigned long long expect;        // flag value of this step
+    unsigned tag;                     // this step's number (never 0)
     int mode;                         // 0: fused (local + peer exchange + global), 1: local part only (NCCL follows)
     // global part
     double* W;                        // k x k rows of the basis at the chosen points (row-major, stride k)
@@ -205,45 +213,43 @@ __device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, doub
     __syncwarp();
 }
 
-// Global part of the tail: `gathered` holds one record per rank.  Runs in one CTA of DEIM_THREADS threads.
-__device__ void deim_tail_global(const TailArgs& a, const double* gathered, double* sbuf) {
-    __shared__ int win_s;
-    __shared__ double wrow[DEIM_BLOCK], w2row[DEIM_SUB];
-    const int tid = threadIdx.x, k = a.k, rec = a.rec;
-    if (tid == 0) {
-        int win = 0;
-        double bv = -1.0, b2 = -1.0;
-        long long bi = MOR_IDX_NONE;
-        for (int r = 0; r < a.nranks; ++r) {
-            const double v = __ldcg(&gathered[(size_t)r * rec]);
-            const long long ix = __double_as_longlong(__ldcg(&gathered[(size_t)r * rec + 1]));
-            const double s = __ldcg(&gathered[(size_t)r * rec + rec - 1]);
-            const long long before = bi;
-            cand_merge(bv, bi, b2, v, ix, s);
-            if (bi != before) win = r;
-        }
-        win_s = win;
-        a.idx_out[a.i] = bi + 1;   // 1-based, like Julia
-        a.values[a.i] = bv;
-        // relative gap to the runner-up: by how much this argmax is decided (0: exact tie / NaN / zero residual)
-        a.margins[a.i] = (bv == bv && bv > 0.0 && b2 >= 0.0) ? (bv - b2) / bv : (bv > 0.0 && b2 < 0.0 ? 1.0 : 0.0);
+// Shared scratch of the tail (one instance per step kernel).
+struct TailSmem {
+    double hv[DEIM_MAXRANKS], h2[DEIM_MAXRANKS];   // every rank's (value, runner-up)
+    long long hi[DEIM_MAXRANKS];                   // ... and global index
+    double st[BST_DOUBLES + SST_DOUBLES];          // the small LU states, prefetched while the candidates reduce
+    long long widx;
+    int win, fail;
+};
+
+// Pick the global winner from the headers (thread 0), record index / value / margin.
+__device__ __forceinline__ void deim_pick_winner(const TailArgs& a, TailSmem& ts) {
+    int win = 0;
+    double bv = -1.0, b2 = -1.0;
+    long long bi = MOR_IDX_NONE;
+    for (int r = 0; r < a.nranks; ++r) {
+        const long long before = bi;
+        cand_merge(bv, bi, b2, ts.hv[r], ts.hi[r], ts.h2[r]);
+        if (bi != before) win = r;
     }
-    __syncthreads();
-    const double* src = gathered + (size_t)win_s * rec;
-    for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = __ldcg(&src[2 + jx]);
+    ts.win = win;
+    a.idx_out[a.i] = bi + 1;   // 1-based, like Julia
+    a.values[a.i] = bv;
+    // relative gap to the runner-up: by how much this argmax is decided (0: exact tie / NaN / zero residual)
+    a.margins[a.i] = (bv == bv && bv > 0.0 && b2 >= 0.0) ? (bv - b2) / bv : (bv > 0.0 && b2 < 0.0 ? 1.0 : 0.0);
+}
+
+// Last part of the tail: `wrec` (shared memory) is the winner's record, ts.st the small LU states.
+__device__ void deim_tail_finish(const TailArgs& a, const double* wrec, TailSmem& ts) {
+    const int tid = threadIdx.x, k = a.k;
+    for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = wrec[2 + jx];
     if (!a.blocked) return;
-    if (tid < DEIM_BLOCK) wrow[tid] = __ldcg(&src[2 + k + tid]);
-    if (tid >= 32 && tid < 32 + DEIM_SUB) w2row[tid - 32] = __ldcg(&src[2 + k + DEIM_BLOCK + tid - 32]);
-    // the small LU states live in global memory between the steps; work on them in shared memory
-    double* bs = sbuf;
-    double* ss = sbuf + BST_DOUBLES;
-    for (int e = tid; e < BST_DOUBLES; e += DEIM_THREADS) bs[e] = __ldcg(&a.bst[e]);
-    if (tid < SST_DOUBLES) ss[tid] = __ldcg(&a.sst[tid]);
-    __syncthreads();
     constexpr int BB = DEIM_BLOCK * DEIM_BLOCK, SS = DEIM_SUB * DEIM_SUB;
+    double* bs = ts.st;
+    double* ss = ts.st + BST_DOUBLES;
     const int warp = tid >> 5;
-    if (warp == 0) bordered_update_warp<DEIM_BLOCK>(bs, bs + BB, bs + 2 * BB, bs + 3 * BB, a.j, a.bw, wrow);
-    if (warp == 1) bordered_update_warp<DEIM_SUB>(ss, ss + SS, ss + 2 * SS, ss + 3 * SS, a.jj, a.sw, w2row);
+    if (warp == 0) bordered_update_warp<DEIM_BLOCK>(bs, bs + BB, bs + 2 * BB, bs + 3 * BB, a.j, a.bw, wrec + 2 + k);
+    if (warp == 1) bordered_update_warp<DEIM_SUB>(ss, ss + SS, ss + 2 * SS, ss + 3 * SS, a.jj, a.sw, wrec + 2 + k + DEIM_BLOCK);
     __syncthreads();
     // the pivot is the residual at the chosen row: exactly zero <=> P'U singular (SingularException in the reference)
     if (tid == 0 && bs[a.j * DEIM_BLOCK + a.j] == 0.0 && !a.last && *a.status == 0) *a.status = a.i + 1;
@@ -262,12 +268,21 @@ __device__ void deim_tail_global(const TailArgs& a, const double* gathered, doub
     }
 }
 
-// The tail, entered by every thread of the LAST CTA of a step kernel.
-__device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2) {
-    __shared__ long long widx_s;
+__device__ __forceinline__ void deim_prefetch_state(const TailArgs& a, TailSmem& ts) {
+    if (!a.blocked) return;
+    for (int e = threadIdx.x; e < BST_DOUBLES; e += DEIM_THREADS) ts.st[e] = __ldcg(&a.bst[e]);
+    if (threadIdx.x < SST_DOUBLES) ts.st[BST_DOUBLES + threadIdx.x] = __ldcg(&a.sst[threadIdx.x]);
+}
+
+// The tail, entered by every thread of the LAST CTA of a step kernel.  sbuf: >= rec doubles of shared memory.
+__device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2, TailSmem& ts) {
     const int tid = threadIdx.x, k = a.k, rec = a.rec;
     unsigned long long t0 = 0;
-    if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    if (tid == 0) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        ts.fail = 0;
+    }
+    deim_prefetch_state(a, ts);
     // (a) this rank's winner over the per-CTA candidates of the launch
     double bv = -1.0, b2 = -1.0;
     long long bi = MOR_IDX_NONE;
@@ -280,27 +295,28 @@ __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long
     __syncthreads();   // sv/si/ss2 were used by the CTA's own reduction
     cand_block_reduce(bv, bi, b2, sv, si, ss2);
     if (tid == 0) {
-        widx_s = bi;
+        ts.widx = bi;
         sbuf[0] = bv;
         sbuf[1] = __longlong_as_double(bi);
         sbuf[rec - 1] = b2;
+        ts.hv[a.rank] = bv;
+        ts.hi[a.rank] = bi;
+        ts.h2[a.rank] = b2;
     }
     __syncthreads();
     // (b) the record: [value, bits(global index), U[idx, 0..k), panel row (16), sub-panel row (4), runner-up]
-    const long long g = widx_s;
+    const long long g = ts.widx;
     for (int jx = tid; jx < k; jx += DEIM_THREADS)
-        sbuf[2 + jx] = (g == MOR_IDX_NONE || jx >= a.kcols) ? 0.0 : a.U[(g - a.row_offset) + (int64_t)jx * a.ldU];
+        sbuf[2 + jx] = (g == MOR_IDX_NONE || jx >= a.kcols) ? 0.0 : __ldcg(&a.U[(g - a.row_offset) + (int64_t)jx * a.ldU]);
     if (a.blocked) {
         if (tid < DEIM_BLOCK)
-            sbuf[2 + k + tid] = (g == MOR_IDX_NONE || tid >= a.bw || a.Pn == nullptr) ? 0.0 : a.Pn[(g - a.row_offset) + (int64_t)tid * a.ldn];
+            sbuf[2 + k + tid] = (g == MOR_IDX_NONE || tid >= a.bw || a.Pn == nullptr) ? 0.0 : __ldcg(&a.Pn[(g - a.row_offset) + (int64_t)tid * a.ldn]);
         if (tid >= 32 && tid < 32 + DEIM_SUB) {
             const int q = tid - 32;
-            sbuf[2 + k + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= a.sw || a.P2 == nullptr) ? 0.0 : a.P2[(g - a.row_offset) + (int64_t)q * a.ld2];
+            sbuf[2 + k + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= a.sw || a.P2 == nullptr) ? 0.0 : __ldcg(&a.P2[(g - a.row_offset) + (int64_t)q * a.ld2]);
         }
     }
     __syncthreads();
-    // (c) publish
-    const size_t slot_off = (size_t)a.slot * a.nranks * rec;
     if (a.mode == 1) {   // NCCL fallback: the host all-gathers `send` and launches deim_tail_global_kernel
         for (int e = tid; e < rec; e += DEIM_THREADS) a.send[e] = sbuf[e];
         if (tid == 0) {
@@ -311,29 +327,44 @@ __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long
         }
         return;
     }
-    const size_t my_off = slot_off + (size_t)a.rank * rec;
-    for (int e = tid; e < rec; e += DEIM_THREADS) {
-        const double v = sbuf[e];
-        for (int p = 0; p < a.nranks; ++p) a.peer_box[p][my_off + e] = v;
-    }
     if (a.nranks > 1) {
-        __threadfence_system();
-        __syncthreads();
+        // (c) publish: this rank's record into every peer's mailbox, slot (step mod 4), region `rank`
+        const size_t my_off = ((size_t)a.slot * DEIM_MAXRANKS + a.rank) * DEIM_REC_MAX;
+        for (int e = tid; e < rec; e += DEIM_THREADS) {
+            const double v = sbuf[e];
+            for (int p = 0; p < a.nranks; ++p)
+                if (p != a.rank) ll_store(a.peer_ll[p] + my_off + e, v, a.tag);
+        }
+        // headers of the other ranks (value, index, runner-up): one thread per rank
+        const long long deadline = clock64() + (1LL << 32);   // ~2 s: a peer died; fail instead of hanging the GPU
         if (tid < a.nranks && tid != a.rank) {
-            st_release_sys(a.peer_flags[tid] + a.slot * DEIM_MAXRANKS + a.rank, a.expect);
-            const unsigned long long* f = a.flags + a.slot * DEIM_MAXRANKS + tid;
-            const long long c0 = clock64();
-            while (ld_acquire_sys(f) != a.expect) {
-                if (clock64() - c0 > (1LL << 32)) {   // ~2 s: a peer died; fail instead of hanging the GPU
-                    atomicExch(a.status, -1);
-                    break;
-                }
-            }
+            const uint4* src = a.ll + ((size_t)a.slot * DEIM_MAXRANKS + tid) * DEIM_REC_MAX;
+            double v = -1.0, ib = 0.0, s2 = -1.0;
+            const bool ok = ll_load(src, a.tag, v, deadline) && ll_load(src + 1, a.tag, ib, deadline) &&
+                            ll_load(src + rec - 1, a.tag, s2, deadline);
+            ts.hv[tid] = v;
+            ts.hi[tid] = ok ? __double_as_longlong(ib) : MOR_IDX_NONE;
+            ts.h2[tid] = s2;
+            if (!ok) ts.fail = 1;
+        }
+        __syncthreads();
+    }
+    // (d) global winner; its record into sbuf
+    if (tid == 0) deim_pick_winner(a, ts);
+    __syncthreads();
+    if (ts.win != a.rank) {
+        const uint4* src = a.ll + ((size_t)a.slot * DEIM_MAXRANKS + ts.win) * DEIM_REC_MAX;
+        const long long deadline = clock64() + (1LL << 32);
+        for (int e = tid; e < rec; e += DEIM_THREADS) {
+            double v = 0.0;
+            if (!ll_load(src + e, a.tag, v, deadline)) ts.fail = 1;
+            sbuf[e] = v;
         }
     }
     __syncthreads();
-    // (d) global winner, factor updates, next coefficients
-    deim_tail_global(a, a.box + slot_off, sbuf);
+    if (tid == 0 && ts.fail) atomicExch(a.status, -1);
+    // (e) factor updates, next coefficients
+    deim_tail_finish(a, sbuf, ts);
     if (tid == 0) {
         *a.ticket = 0;
         unsigned long long t1;
@@ -352,9 +383,23 @@ __device__ __forceinline__ bool deim_last_cta(unsigned* ticket) {
     return last_s != 0;
 }
 
+// NCCL fallback: the global part of the tail as its own launch; `gathered` = nranks plain records.
 __global__ void __launch_bounds__(DEIM_THREADS) deim_tail_global_kernel(TailArgs a, const double* gathered) {
     __shared__ double sbuf[SBUF_DOUBLES];
-    deim_tail_global(a, gathered, sbuf);
+    __shared__ TailSmem ts;
+    const int tid = threadIdx.x, rec = a.rec;
+    deim_prefetch_state(a, ts);
+    if (tid < a.nranks) {
+        ts.hv[tid] = gathered[(size_t)tid * rec];
+        ts.hi[tid] = __double_as_longlong(gathered[(size_t)tid * rec + 1]);
+        ts.h2[tid] = gathered[(size_t)tid * rec + rec - 1];
+    }
+    __syncthreads();
+    if (tid == 0) deim_pick_winner(a, ts);
+    __syncthreads();
+    for (int e = tid; e < rec; e += DEIM_THREADS) sbuf[e] = gathered[(size_t)ts.win * rec + e];
+    __syncthreads();
+    deim_tail_finish(a, sbuf, ts);
 }
 
 // Fused residual + abs-argmax over this rank's rows, then the tail.  l = number of previous columns.
@@ -457,7 +502,8 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l, con
         ta.cands[blockIdx.x].val2 = b2;
     }
     if (!deim_last_cta(ta.ticket)) return;
-    deim_tail(ta, sc, sv, si, ss2);
+    __shared__ TailSmem ts;
+    deim_tail(ta, sc, sv, si, ss2, ts);
 }
 
 // Second blocking level: residuals of the next sw <= 4 columns of a panel P1 with respect to the s0 <= 12
@@ -550,7 +596,8 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
         ta.cands[blockIdx.x].val2 = b2;
     }
     if (!deim_last_cta(ta.ticket)) return;   // includes the fence that publishes this CTA's R2 stores
-    deim_tail(ta, sbuf, sv, si, ss2);
+    __shared__ TailSmem ts;
+    deim_tail(ta, sbuf, sv, si, ss2, ts);
 }
 
 __device__ __forceinline__ double warp_sum(double s) {
@@ -661,29 +708,35 @@ deim_gather_block_kernel(const double* __restrict__ U, int64_t m, int64_t ld, in
 }
 
 // Coefficients of the panel that starts at column l0:  C = A[0:l0, 0:l0] * W12  (column q of C solves
-// (P'U_l0) c = P'u_{l0+q}, deim.jl:21).  W12[s][q] = Wsrc[s * ldw + q].  One CTA per 16-row slab; written twice:
-// packed for deim_panel_kernel, Cp[c][q][kk] = C[16 c + kk][q], and plain (C12[t * 16 + q]) for the panel-end update.
-__global__ void __launch_bounds__(DEIM_BLOCK * 20)
+// (P'U_l0) c = P'u_{l0+q}, deim.jl:21).  W12[s][q] = Wsrc[s * ldw + q].  One warp per row t of C: the lanes split the
+// dot products (row t of A is contiguous, row s of W12 is 16 contiguous doubles), 16 partial sums per lane are
+// combined by shuffles -- a latency chain of l0 / 32 loads instead of l0.  Written twice: packed for
+// deim_panel_kernel, Cp[c][q][kk] = C[16 c + kk][q] (the host zeroes the padding once), and plain (C12[t * 16 + q])
+// for the panel-end update.
+__global__ void __launch_bounds__(256)
 deim_coef_kernel(const double* __restrict__ A, int k, int l0, int bw, const double* __restrict__ Wsrc, int ldw,
                  double* __restrict__ Cp, double* __restrict__ C12) {
-    const int e = threadIdx.x, q = e / 20, kk = e % 20;
-    const int t = blockIdx.x * DEIM_BLOCK + kk;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (kk < DEIM_BLOCK && q < bw && t < l0) {
-        const double* a = A + (size_t)t * k;
-        const double* w = Wsrc + q;
-        int r = 0;
-        for (; r + 4 <= l0; r += 4) {
-            s0 = fma(a[r], w[(size_t)r * ldw], s0);
-            s1 = fma(a[r + 1], w[(size_t)(r + 1) * ldw], s1);
-            s2 = fma(a[r + 2], w[(size_t)(r + 2) * ldw], s2);
-            s3 = fma(a[r + 3], w[(size_t)(r + 3) * ldw], s3);
-        }
-        for (; r < l0; ++r) s0 = fma(a[r], w[(size_t)r * ldw], s0);
+    const int lane = threadIdx.x & 31, t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= l0) return;
+    double acc[DEIM_BLOCK];
+#pragma unroll
+    for (int q = 0; q < DEIM_BLOCK; ++q) acc[q] = 0.0;
+    const double* a = A + (size_t)t * k;
+    for (int r = lane; r < l0; r += 32) {
+        const double av = __ldcg(&a[r]);
+        const double* w = Wsrc + (size_t)r * ldw;
+#pragma unroll
+        for (int q = 0; q < DEIM_BLOCK; ++q) acc[q] = fma(av, q < bw ? __ldcg(&w[q]) : 0.0, acc[q]);
     }
-    const double v = (s0 + s1) + (s2 + s3);
-    Cp[(size_t)blockIdx.x * (DEIM_BLOCK * 20) + e] = v;
-    if (kk < DEIM_BLOCK && t < l0) C12[t * DEIM_BLOCK + q] = v;
+#pragma unroll
+    for (int q = 0; q < DEIM_BLOCK; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane < DEIM_BLOCK) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < DEIM_BLOCK; ++q) v = (q == lane) ? acc[q] : v;
+        Cp[(size_t)(t / DEIM_BLOCK) * (DEIM_BLOCK * 20) + lane * 20 + (t % DEIM_BLOCK)] = v;
+        C12[t * DEIM_BLOCK + lane] = v;
+    }
 }
 
 // Panel end, step 1: Sinv = inv(S) = Z * inv(L) of the panel's pivot block S = P'R = L * Uf (16 x 16, unit lower L),
@@ -714,37 +767,42 @@ deim_sinv_kernel(const double* __restrict__ bst, int bw, int k, int l0, double* 
 }
 
 // Panel end, step 2: F = Sinv * (W21 * A11)  (bw x l0), W21 = W[l0:l0+bw, 0:l0]; also A21 = -F.
-// One thread per column j of A11; W21 is staged through shared memory in chunks of 64 rows of A.
-__global__ void __launch_bounds__(64)
+// One CTA per 16 columns j of A11: thread (ts, jj) accumulates rows t = ts (mod 16) of all 16 dot products of its
+// column (A[t][j] is read once, coalesced over jj), the 16 slices are summed through shared memory.
+__global__ void __launch_bounds__(256)
 deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W, int k, int l0, int bw,
                   const double* __restrict__ Sinv, double* __restrict__ F) {
-    __shared__ double w21[DEIM_BLOCK][64], sinv[DEIM_BLOCK * DEIM_BLOCK];
-    const int tid = threadIdx.x, j = blockIdx.x * 64 + tid;
-    for (int e = tid; e < DEIM_BLOCK * DEIM_BLOCK; e += 64) sinv[e] = Sinv[e];
+    __shared__ double part[DEIM_BLOCK][DEIM_BLOCK][DEIM_BLOCK + 1];   // [slice][c][jj]
+    __shared__ double e[DEIM_BLOCK][DEIM_BLOCK + 1], sinv[DEIM_BLOCK * DEIM_BLOCK];
+    const int tid = threadIdx.x, jj = tid % DEIM_BLOCK, ts = tid / DEIM_BLOCK, j = blockIdx.x * DEIM_BLOCK + jj;
+    sinv[tid] = Sinv[tid];
     double acc[DEIM_BLOCK];
 #pragma unroll
     for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = 0.0;
-    for (int t0 = 0; t0 < l0; t0 += 64) {
-        __syncthreads();
-        for (int c = 0; c < DEIM_BLOCK; ++c)
-            w21[c][tid] = (c < bw && t0 + tid < l0) ? W[(size_t)(l0 + c) * k + t0 + tid] : 0.0;
-        __syncthreads();
-        const int tn = l0 - t0 < 64 ? l0 - t0 : 64;
-        if (j < l0)
-            for (int t = 0; t < tn; ++t) {
-                const double av = A[(size_t)(t0 + t) * k + j];
+    if (j < l0)
+        for (int t = ts; t < l0; t += DEIM_BLOCK) {
+            const double av = __ldcg(&A[(size_t)t * k + j]);
 #pragma unroll
-                for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = fma(w21[c][t], av, acc[c]);
-            }
-    }
-    if (j >= l0) return;
-    for (int c = 0; c < bw; ++c) {
+            for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = fma(c < bw ? __ldcg(&W[(size_t)(l0 + c) * k + t]) : 0.0, av, acc[c]);
+        }
+#pragma unroll
+    for (int c = 0; c < DEIM_BLOCK; ++c) part[ts][c][jj] = acc[c];
+    __syncthreads();
+    {
+        const int c = ts;   // thread (c, jj) sums the slices of E[c][j]
         double s = 0.0;
 #pragma unroll
-        for (int c2 = 0; c2 < DEIM_BLOCK; ++c2) s = fma(sinv[c * DEIM_BLOCK + c2], acc[c2], s);
-        F[(size_t)c * k + j] = s;
-        A[(size_t)(l0 + c) * k + j] = -s;
+        for (int sl = 0; sl < DEIM_BLOCK; ++sl) s += part[sl][c][jj];
+        e[c][jj] = s;
     }
+    __syncthreads();
+    const int c = ts;
+    if (j >= l0 || c >= bw) return;
+    double s = 0.0;
+#pragma unroll
+    for (int c2 = 0; c2 < DEIM_BLOCK; ++c2) s = fma(sinv[c * DEIM_BLOCK + c2], e[c2][jj], s);
+    F[(size_t)c * k + j] = s;
+    A[(size_t)(l0 + c) * k + j] = -s;
 }
 
 // Panel end, step 3: A11 += C12 * F (rank-bw update), A12 = -C12 * Sinv.  One thread per entry of the l0 x (l0 + bw) block.
@@ -878,12 +936,8 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     ta.ldU = ld;
     ta.k = (int)k;
     ta.row_offset = row_offset;
-    ta.box = cx.box;
-    ta.flags = cx.box_flags;
-    for (int r = 0; r < cx.nranks; ++r) {
-        ta.peer_box[r] = fused ? cx.peer_box[r] : cx.box;
-        ta.peer_flags[r] = fused ? cx.peer_flags[r] : cx.box_flags;
-    }
+    ta.ll = cx.box_ll;
+    for (int r = 0; r < cx.nranks; ++r) ta.peer_ll[r] = fused ? cx.peer_ll[r] : cx.box_ll;
     ta.send = cx.box + (size_t)DEIM_SLOTS * DEIM_MAXRANKS * DEIM_REC_MAX;
     ta.rank = cx.rank;
     ta.nranks = cx.nranks;
@@ -929,7 +983,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
                 wsrc = W12;
                 ldw = DEIM_BLOCK;
             }
-            deim_coef_kernel<<<l0 / DEIM_BLOCK, DEIM_BLOCK * 20, 0, cx.stream>>>(A, (int)k, l0, bw, wsrc, ldw, Cp, C12);
+            deim_coef_kernel<<<(l0 + 7) / 8, 256, 0, cx.stream>>>(A, (int)k, l0, bw, wsrc, ldw, Cp, C12);
             count_launch();
             t_upd.stop();
             t_panel.start();
@@ -950,7 +1004,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
         ta.last = i == (int)k - 1 ? 1 : 0;
         const unsigned long long seq = cx.deim_seq + (unsigned long long)i;
         ta.slot = (int)(seq % DEIM_SLOTS);
-        ta.expect = seq + 1;
+        ta.tag = (unsigned)(seq % 0xfffffff0ull) + 1u;   // never 0 (a zeroed mailbox matches no step)
         if (blocked && s0 > 0 && jj == 0) {
             // residuals of the next 4 panel columns in one pass over the s0 earlier ones, fused with this step's argmax
             deim_step4_kernel<R><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, s0, sw, Dsub, R2, ldp, row_offset, ta);
@@ -977,7 +1031,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             t_upd.start();
             deim_sinv_kernel<<<1, DEIM_BLOCK * DEIM_BLOCK, 0, cx.stream>>>(bst, bw, (int)k, l0, Sinv, A);
             if (l0 > 0) {
-                deim_inv_f_kernel<<<(l0 + 63) / 64, 64, 0, cx.stream>>>(A, W, (int)k, l0, bw, Sinv, Fm);
+                deim_inv_f_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(A, W, (int)k, l0, bw, Sinv, Fm);
                 deim_inv_update_kernel<<<dim3((l0 + bw + 15) / 16, (l0 + 15) / 16), 256, 0, cx.stream>>>(A, (int)k, l0, bw, C12,
                                                                                                    Fm, Sinv);
                 count_launch(2);
@@ -987,7 +1041,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
         }
     }
     t_total.stop();
-    cx.deim_seq += (unsigned long long)k;
+    if (cx.nranks > 1) cx.deim_seq += (unsigned long long)k;   // a one-rank (solo) call must not desynchronise the ranks' step counters
     MOR_CUDA(cudaGetLastError());
     std::vector<long long> idx_h((size_t)k);
     cx.deim_margins.assign((size_t)k, 0.0);
@@ -1098,6 +1152,7 @@ extern "C" {
 
 int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx, mor_mat_t P_out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_deim_projector_dev(U, V, idx, P_out));
     MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector_dev: null argument");
     MOR_ARG(U->m == V->m && P_out->m == V->n && P_out->n == U->n, "mor_b200_deim_projector_dev: P_out must be pod_dim x deim_dim");
     MOR_TRY(require_ctx());
@@ -1107,6 +1162,7 @@ int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx
 int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp,
                                 int64_t ldv, const int64_t* idx, double* P_out, int64_t ldp) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_deim_projector(U, m, kd, ldu, V, kp, ldv, idx, P_out, ldp);
     MOR_ARG(U && V && idx && P_out, "mor_b200_deim_projector: null pointer");
     MOR_ARG(m >= 0 && kd >= 1 && kp >= 1 && ldu >= (m > 0 ? m : 1) && ldv >= (m > 0 ? m : 1) && ldp >= kp,
             "mor_b200_deim_projector: bad dimensions");
@@ -1149,6 +1205,7 @@ int32_t mor_b200_deim_last_margins(double* margins, double* values, int64_t cap,
 
 int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_deim_indices_dev(B, idx_out));
     MOR_ARG(B != nullptr, "mor_b200_deim_indices_dev: null matrix");
     MOR_TRY(require_ctx());
     return deim_indices_device(B->p, B->m, B->n, B->ld, idx_out);
@@ -1156,6 +1213,7 @@ int32_t mor_b200_deim_indices_dev(mor_mat_t B, int64_t* idx_out) {
 
 int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_deim_indices(B, m, k, ldb, idx_out);
     MOR_ARG(B != nullptr && idx_out != nullptr, "mor_b200_deim_indices: null pointer");
     MOR_ARG(m >= 0 && k >= 1 && ldb >= (m > 0 ? m : 1), "mor_b200_deim_indices: bad dimensions");
     MOR_TRY(require_ctx());
@@ -1180,10 +1238,7 @@ int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb
         cu(cudaEventRecord(ev[(size_t)ngroups], cx.aux_stream), "cudaEventRecord");
         for (int g = 0; g < ngroups && st == MOR_OK; ++g) {
             const int64_t c0 = (int64_t)g * GROUP, nc = k - c0 < GROUP ? k - c0 : GROUP;
-            if (m > 0)
-                cu(cudaMemcpy2DAsync(d->p + (size_t)c0 * d->ld, (size_t)d->ld * 8, B + (size_t)c0 * ldb, (size_t)ldb * 8,
-                                     (size_t)m * 8, (size_t)nc, cudaMemcpyHostToDevice, cx.aux_stream),
-                   "cudaMemcpy2DAsync(basis columns)");
+            if (m > 0 && st == MOR_OK) st = h2d_2d(d->p + (size_t)c0 * d->ld, d->ld, B + (size_t)c0 * ldb, ldb, m, nc, cx.aux_stream);
             cu(cudaEventRecord(ev[(size_t)g], cx.aux_stream), "cudaEventRecord");
         }
     }

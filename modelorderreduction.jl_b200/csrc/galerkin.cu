@@ -68,6 +68,7 @@ extern "C" {
 int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                               const double* V, int64_t k, int64_t ldv, double* Ahat, int64_t lda) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_galerkin_csc(m, colptr, rowval, nzval, V, k, ldv, Ahat, lda));
     MOR_ARG(colptr && V && Ahat && m >= 1 && k >= 1 && ldv >= m && lda >= k, "mor_b200_galerkin_csc: bad arguments");
     MOR_ARG(colptr[0] == 1 && colptr[m] >= 1, "mor_b200_galerkin_csc: colptr must be 1-based (Julia SparseMatrixCSC)");
     const int64_t nnz = colptr[m] - 1;
@@ -105,6 +106,7 @@ int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* r
 int32_t mor_b200_project(const double* V, int64_t m, int64_t k, int64_t ldv, const double* Xv, int64_t nvec,
                          int64_t ldx, double* out, int64_t ldo) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_project(V, m, k, ldv, Xv, nvec, ldx, out, ldo);
     MOR_ARG(V && Xv && out && m >= 0 && k >= 1 && nvec >= 1, "mor_b200_project: bad arguments");
     MOR_ARG(ldv >= (m > 0 ? m : 1) && ldx >= (m > 0 ? m : 1) && ldo >= k && k <= 4096 && nvec <= 4096,
             "mor_b200_project: bad dimensions");

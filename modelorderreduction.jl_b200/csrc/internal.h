@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -52,30 +53,94 @@ struct Ctx {
     size_t ingest_bytes = 0;            // cudaMalloc/cudaFree of 137 GB cost ~0.4 s per call otherwise
     // DEIM exchange mailbox (deim.cu, nccl.cpp): per greedy step every rank stores its candidate record into every
     // peer's mailbox over NVLink and raises a flag there -- no NCCL call on the 256-step latency chain
-    void* box_base = nullptr;           // one cudaMalloc: flags | ticket | records
+    void* box_base = nullptr;           // one cudaMalloc: header (ticket) | plain records (NCCL fallback) | tagged words
     double* box = nullptr;
-    unsigned long long* box_flags = nullptr;
+    uint4* box_ll = nullptr;
     unsigned* box_ticket = nullptr;
     void* peer_base[8] = {nullptr};     // peers' mailboxes mapped into this process (CUDA IPC) or this device (P2P)
-    double* peer_box[8] = {nullptr};
-    unsigned long long* peer_flags[8] = {nullptr};
+    uint4* peer_ll[8] = {nullptr};
     bool peers_tried = false, peers_ok = false, peers_ipc = false;
     unsigned long long deim_seq = 0;    // greedy steps taken since comm_init (the same on every rank): slot / flag value
     std::vector<double> deim_margins;   // relative gap to the runner-up at every greedy step of the last call
     std::vector<double> deim_values;    // the winning residual of every greedy step of the last call
+    // pageable-host ingest (ingest.cpp): ring of pinned staging buffers filled by a few host copy threads
+    static constexpr int NSTAGE = 4;
+    void* stage_buf[NSTAGE] = {nullptr};
+    cudaEvent_t stage_ev[NSTAGE] = {nullptr};
+    bool stage_busy[NSTAGE] = {false};
+    int stage_next = 0;
+    void* copy_pool = nullptr;
+    bool last_ingest_staged = false;    // the last host -> device transfer went through the staging ring
 };
 // mailbox geometry (shared by deim.cu and nccl.cpp)
 constexpr int MBOX_SLOTS = 4, MBOX_MAXRANKS = 8, MBOX_REC_MAX = 1024 + 16 + 4 + 3;
-constexpr size_t MBOX_HEADER_BYTES = 1024;   // flags (SLOTS x MAXRANKS u64) then the ticket at byte 512
-constexpr size_t MBOX_BYTES = MBOX_HEADER_BYTES + sizeof(double) * (size_t)(MBOX_SLOTS * MBOX_MAXRANKS + 1) * MBOX_REC_MAX;
+constexpr size_t MBOX_HEADER_BYTES = 1024;   // the ticket at byte 512
+constexpr size_t MBOX_PLAIN_BYTES = (sizeof(double) * (size_t)(MBOX_SLOTS * MBOX_MAXRANKS + 1) * MBOX_REC_MAX + 255) & ~size_t(255);
+constexpr size_t MBOX_LL_BYTES = 16 * (size_t)(MBOX_SLOTS * MBOX_MAXRANKS) * MBOX_REC_MAX;
+constexpr size_t MBOX_BYTES = MBOX_HEADER_BYTES + MBOX_PLAIN_BYTES + MBOX_LL_BYTES;
 int32_t deim_mailbox();   // allocate the own mailbox; with several ranks, map the peers' (all ranks or none)
 void deim_mailbox_release();
+void stage_release();       // pinned staging ring of the pageable-host ingest (ingest.cpp)
+bool host_is_pinned(const void* p);
+// column-major 2-D transfers; a page-locked host pointer goes to the DMA engine directly, a pageable one through the
+// staging ring.  h2d is asynchronous on `st` (the host thread is busy while it fills staging buffers); d2h returns
+// when the data is in place.
+int32_t h2d_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st);
+int32_t d2h_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st);
+void multi_skip_env();
+const std::string& last_error_string();
+// The context of the calling thread: the process-wide one (one process per GPU), or -- inside a worker thread of the
+// single-process multi-GPU mode (multi.cpp) -- the context of that worker's GPU.
 Ctx& ctx();
+Ctx& ctx_of(int r);          // multi mode: the context of rank r
+void bind_ctx(int r);        // worker threads: make ctx() mean rank r's context
+int32_t init_device(Ctx& c, int device);
+void teardown_device(Ctx& c);
 int32_t require_ctx();
 // Every public entry point holds this (recursive: entry points call each other) for its duration:
-// calls from several host threads are safe and simply serialise on the one per-process context.
+// calls from several host threads are safe and simply serialise.  Worker threads of the multi-GPU mode only run
+// while the dispatching thread holds the lock, so for them it is a no-op.
 std::recursive_mutex& api_mutex();
-#define MOR_API_LOCK std::lock_guard<std::recursive_mutex> api_lock__(::mor::api_mutex())
+bool is_worker();
+struct ApiLock {
+    bool held;
+    ApiLock() : held(!is_worker()) {
+        if (held) api_mutex().lock();
+    }
+    ~ApiLock() {
+        if (held) api_mutex().unlock();
+    }
+    ApiLock(const ApiLock&) = delete;
+    ApiLock& operator=(const ApiLock&) = delete;
+};
+#define MOR_API_LOCK ::mor::ApiLock api_lock__
+
+// ---- single-process multi-GPU mode (multi.cpp): mor_b200_init_multi / MOR_B200_NGPUS ----------------------------
+bool multi_on();             // true once init_multi succeeded (also performs the lazy MOR_B200_NGPUS start-up)
+int multi_n();
+int32_t multi_shutdown();
+int32_t multi_solo(const std::function<int32_t()>& fn);          // run on GPU 0 as a single-rank job
+int32_t multi_all(const std::function<int32_t(int)>& fn);        // run on every GPU's worker thread, first error wins
+void multi_shard(int64_t m, int r, int64_t* row0, int64_t* rows);  // contiguous row ranges, starts on multiples of 4
+}  // namespace mor
+struct mor_pod_s;
+namespace mor {
+int32_t multi_pod_factor(const double* X, const double* const* cols, int64_t m, int64_t n, int64_t ldx, int32_t method,
+                         int64_t k, int64_t p, const double* Omega, uint64_t seed, mor_pod_s** handle, double* S_out,
+                         int64_t* nS);
+int32_t multi_pod_basis(mor_pod_s* h, int64_t k, double* U_out, int64_t ldu, double* V_out, int64_t ldv);
+int32_t multi_pod_free(mor_pod_s* h);
+int32_t multi_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out);
+int32_t multi_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp, int64_t ldv,
+                             const int64_t* idx, double* P_out, int64_t ldp);
+int32_t multi_project(const double* V, int64_t m, int64_t k, int64_t ldv, const double* Xv, int64_t nvec, int64_t ldx,
+                      double* out, int64_t ldo);
+// entry points that only make sense on one device (device-resident API, single-rank helpers): in multi mode GPU 0
+#define MOR_ROUTE_SOLO(call)                                                                  \
+    do {                                                                                      \
+        if (::mor::multi_on() && !::mor::is_worker())                                          \
+            return ::mor::multi_solo([&]() -> int32_t { return call; });                      \
+    } while (0)
 inline void count_launch(int n = 1) { ctx().launches += n; }
 // Grow-only device workspace of at least `bytes`; contents are only valid until the next
 // scratch() call on this context (all users are ordered on ctx().stream).
@@ -133,6 +198,27 @@ struct mor_mat_s {
     double* p = nullptr;
     int64_t m = 0, n = 0, ld = 0;
     bool owned = false;
+};
+
+// ---- factorisation handle ---------------------------------------------------------------------
+struct mor_pod_s {
+    int64_t m = 0, n = 0;       // this rank's shard of the input X is m x n
+    int64_t m_global = 0;
+    bool wide = false;          // T = X' was factored (single rank)
+    int method = MOR_SVD;
+    // tall side: left vectors of T are T * M(:, 0:k)
+    double* T = nullptr;
+    int64_t trows = 0, ldt = 0;
+    int tn = 0;                 // columns of T = rows of M
+    mor::DevBuf T_owned;        // set when the library owns T
+    mor::DevBuf M;              // tn x r, ld = tn
+    mor::DevBuf Vs;             // vs_rows x r, ld = vs_rows: small-side (right) vectors of T
+    int vs_rows = 0, r = 0;     // r = singular triplets available
+    std::vector<double> sigma;  // r values, descending
+    int passes = 0, sweeps = 0;
+    // single-process multi-GPU mode: one per-GPU handle per rank and the row range each one holds
+    std::vector<mor_pod_s*> parts;
+    std::vector<int64_t> part_row0, part_rows;
 };
 
 namespace mor {

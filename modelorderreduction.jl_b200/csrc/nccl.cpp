@@ -116,12 +116,11 @@ int32_t comm_allgather_i64(int64_t mine, std::vector<int64_t>& all) {
 // ---- DEIM mailbox: the per-step candidate exchange goes over peer memory, not through NCCL ------------------------
 static void mailbox_set_pointers(Ctx& c) {
     unsigned char* b = static_cast<unsigned char*>(c.box_base);
-    c.box_flags = reinterpret_cast<unsigned long long*>(b);
     c.box_ticket = reinterpret_cast<unsigned*>(b + 512);
     c.box = reinterpret_cast<double*>(b + MBOX_HEADER_BYTES);
+    c.box_ll = reinterpret_cast<uint4*>(b + MBOX_HEADER_BYTES + MBOX_PLAIN_BYTES);
     c.peer_base[c.rank] = c.box_base;
-    c.peer_box[c.rank] = c.box;
-    c.peer_flags[c.rank] = c.box_flags;
+    c.peer_ll[c.rank] = c.box_ll;
 }
 
 void deim_mailbox_release() {
@@ -129,13 +128,12 @@ void deim_mailbox_release() {
     for (int r = 0; r < MBOX_MAXRANKS; ++r) {
         if (c.peers_ipc && c.peer_base[r] && c.peer_base[r] != c.box_base) cudaIpcCloseMemHandle(c.peer_base[r]);
         c.peer_base[r] = nullptr;
-        c.peer_box[r] = nullptr;
-        c.peer_flags[r] = nullptr;
+        c.peer_ll[r] = nullptr;
     }
     if (c.box_base) cudaFree(c.box_base);
     c.box_base = nullptr;
     c.box = nullptr;
-    c.box_flags = nullptr;
+    c.box_ll = nullptr;
     c.box_ticket = nullptr;
     c.peers_tried = c.peers_ok = c.peers_ipc = false;
     c.deim_seq = 0;
@@ -195,8 +193,7 @@ int32_t deim_mailbox() {
         if (r == c.rank) continue;
         unsigned char* b = static_cast<unsigned char*>(mapped[r]);
         c.peer_base[r] = mapped[r];
-        c.peer_flags[r] = reinterpret_cast<unsigned long long*>(b);
-        c.peer_box[r] = reinterpret_cast<double*>(b + MBOX_HEADER_BYTES);
+        c.peer_ll[r] = reinterpret_cast<uint4*>(b + MBOX_HEADER_BYTES + MBOX_PLAIN_BYTES);
     }
     c.peers_ipc = true;
     c.peers_ok = true;
@@ -223,6 +220,10 @@ int32_t mor_b200_comm_unique_id(void* id128) {
 int32_t mor_b200_comm_init(int32_t rank, int32_t nranks, const void* id128) {
     MOR_API_LOCK;
     MOR_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "mor_b200_comm_init: bad rank/nranks");
+    if (multi_on() && !is_worker()) {
+        set_error("mor_b200_comm_init: the library is in single-process multi-GPU mode; it owns the communicator");
+        return MOR_ERR_ARG;
+    }
     MOR_TRY(require_ctx());
     Ctx& c = ctx();
     if (c.comm) mor_b200_comm_destroy();
@@ -253,6 +254,7 @@ int32_t mor_b200_comm_info(int32_t* rank, int32_t* nranks) {
 
 int32_t mor_b200_comm_destroy(void) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return MOR_OK;   // the workers' communicators go with mor_b200_shutdown
     Ctx& c = ctx();
     if (c.comm && g_nccl.CommDestroy) {
         if (c.ready) {

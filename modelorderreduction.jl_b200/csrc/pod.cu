@@ -20,23 +20,6 @@
 
 #include "internal.h"
 
-struct mor_pod_s {
-    int64_t m = 0, n = 0;       // this rank's shard of the input X is m x n
-    int64_t m_global = 0;
-    bool wide = false;          // T = X' was factored (single rank)
-    int method = MOR_SVD;
-    // tall side: left vectors of T are T * M(:, 0:k)
-    double* T = nullptr;
-    int64_t trows = 0, ldt = 0;
-    int tn = 0;                 // columns of T = rows of M
-    mor::DevBuf T_owned;        // set when the library owns T
-    mor::DevBuf M;              // tn x r, ld = tn
-    mor::DevBuf Vs;             // vs_rows x r, ld = vs_rows: small-side (right) vectors of T
-    int vs_rows = 0, r = 0;     // r = singular triplets available
-    std::vector<double> sigma;  // r values, descending
-    int passes = 0, sweeps = 0;
-};
-
 namespace mor {
 namespace {
 
@@ -525,6 +508,7 @@ extern "C" {
 int32_t mor_b200_pod_factor_dev(mor_mat_t X, int32_t method, int64_t k, int64_t p, mor_mat_t Omega, uint64_t seed,
                                 int32_t flags, mor_pod_t* handle, double* S_out, int64_t* nS) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_pod_factor_dev(X, method, k, p, Omega, seed, flags, handle, S_out, nS));
     MOR_ARG(X != nullptr, "mor_b200_pod_factor_dev: null matrix");
     MOR_TRY(require_ctx());
     MOR_ARG(X->ld % 2 == 0 && (uintptr_t)X->p % 16 == 0,
@@ -577,8 +561,7 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
         tm.gram.start();
         for (int64_t r0 = 0; r0 < m; r0 += ch) {
             const int64_t rc = std::min(ch, m - r0);
-            MOR_CUDA(cudaMemcpy2DAsync(dX.as<double>() + r0, (size_t)ld * 8, X + r0, (size_t)ldx * 8, (size_t)rc * 8,
-                                       (size_t)n, cudaMemcpyHostToDevice, cx.copy_stream));
+            MOR_TRY(h2d_2d(dX.as<double>() + r0, ld, X + r0, ldx, rc, n, cx.copy_stream));
             cudaEvent_t ev;
             MOR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             MOR_CUDA(cudaEventRecord(ev, cx.copy_stream));
@@ -593,12 +576,10 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
         if (cols) {
             for (int64_t j = 0; j < n; ++j) {
                 MOR_ARG(cols[j] != nullptr, "mor_b200_pod_factor_cols: null column pointer");
-                MOR_CUDA(cudaMemcpyAsync(dX.as<double>() + (size_t)j * ld, cols[j], sizeof(double) * (size_t)m,
-                                         cudaMemcpyHostToDevice, cx.stream));
+                MOR_TRY(h2d_2d(dX.as<double>() + (size_t)j * ld, ld, cols[j], m, m, 1, cx.stream));
             }
         } else {
-            MOR_CUDA(cudaMemcpy2DAsync(dX.p, (size_t)ld * 8, X, (size_t)ldx * 8, (size_t)m * 8, (size_t)n,
-                                       cudaMemcpyHostToDevice, cx.stream));
+            MOR_TRY(h2d_2d(dX.as<double>(), ld, X, ldx, m, n, cx.stream));
         }
         tm.h2d.stop();
     }
@@ -622,6 +603,7 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
 int32_t mor_b200_pod_factor(const double* X, int64_t m, int64_t n, int64_t ldx, int32_t method, int64_t k, int64_t p,
                             const double* Omega, uint64_t seed, mor_pod_t* handle, double* S_out, int64_t* nS) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_pod_factor(X, nullptr, m, n, ldx, method, k, p, Omega, seed, handle, S_out, nS);
     return factor_from_host(X, nullptr, m, n, ldx, method, k, p, Omega, seed, handle, S_out, nS);
 }
 
@@ -629,12 +611,14 @@ int32_t mor_b200_pod_factor_cols(const double* const* cols, int64_t m, int64_t n
                                  int64_t p, const double* Omega, uint64_t seed, mor_pod_t* handle, double* S_out,
                                  int64_t* nS) {
     MOR_API_LOCK;
+    if (multi_on() && !is_worker()) return multi_pod_factor(nullptr, cols, m, n, m, method, k, p, Omega, seed, handle, S_out, nS);
     MOR_ARG(cols != nullptr, "mor_b200_pod_factor_cols: null pointer");
     return factor_from_host(nullptr, cols, m, n, m, method, k, p, Omega, seed, handle, S_out, nS);
 }
 
 int32_t mor_b200_pod_basis_dev(mor_pod_t h, int64_t k, mor_mat_t U_out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_pod_basis_dev(h, k, U_out));
     MOR_ARG(h != nullptr && U_out != nullptr, "mor_b200_pod_basis_dev: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_basis_dev: k must be in 1..number of computed triplets");
     MOR_ARG(U_out->m == h->m && U_out->n >= k, "mor_b200_pod_basis_dev: U_out must be m x >= k");
@@ -658,6 +642,7 @@ int32_t mor_b200_pod_basis_dev(mor_pod_t h, int64_t k, mor_mat_t U_out) {
 
 int32_t mor_b200_pod_right_dev(mor_pod_t h, int64_t k, mor_mat_t V_out) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_pod_right_dev(h, k, V_out));
     MOR_ARG(h != nullptr && V_out != nullptr, "mor_b200_pod_right_dev: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_right_dev: k must be in 1..number of computed triplets");
     MOR_ARG(V_out->m == h->n && V_out->n >= k, "mor_b200_pod_right_dev: V_out must be n x >= k");
@@ -679,6 +664,7 @@ int32_t mor_b200_pod_right_dev(mor_pod_t h, int64_t k, mor_mat_t V_out) {
 
 int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, double* V_out, int64_t ldv) {
     MOR_API_LOCK;
+    if (h != nullptr && multi_on() && !is_worker()) return multi_pod_basis(h, k, U_out, ldu, V_out, ldv);
     MOR_ARG(h != nullptr && U_out != nullptr, "mor_b200_pod_basis: null argument");
     MOR_ARG(k >= 1 && k <= h->r, "mor_b200_pod_basis: k must be in 1..number of computed triplets");
     MOR_ARG(ldu >= std::max<int64_t>(h->m, 1) && (!V_out || ldv >= h->n), "mor_b200_pod_basis: leading dimension too small");
@@ -698,10 +684,8 @@ int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, d
         MOR_TRY(dU.alloc(sizeof(double) * (size_t)ldd * (size_t)k));
         MOR_TRY(tall_vectors(h, (int)k, dU.as<double>(), ldd, tm));
         tm.d2h.start();
-        MOR_CUDA(cudaMemcpy2DAsync(tall_host, (size_t)tall_ld * 8, dU.p, (size_t)ldd * 8, (size_t)h->trows * 8,
-                                   (size_t)k, cudaMemcpyDeviceToHost, cx.stream));
+        MOR_TRY(d2h_2d(tall_host, tall_ld, dU.as<double>(), ldd, h->trows, k, cx.stream));
         tm.d2h.stop();
-        MOR_CUDA(cudaStreamSynchronize(cx.stream));
     }
     if (small_host) {
         tm.d2h.start();
@@ -718,6 +702,7 @@ int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, d
 
 int32_t mor_b200_pod_free(mor_pod_t h) {
     MOR_API_LOCK;
+    if (h != nullptr && multi_on() && !is_worker()) return multi_pod_free(h);
     if (!h) return MOR_OK;
     if (ctx().ready) {
         cudaSetDevice(ctx().device);
@@ -729,6 +714,7 @@ int32_t mor_b200_pod_free(mor_pod_t h) {
 
 int32_t mor_b200_pod_info(mor_pod_t h, int32_t* passes, int32_t* sweeps) {
     MOR_ARG(h != nullptr, "mor_b200_pod_info: null handle");
+    if (!h->parts.empty()) h = h->parts[0];
     if (passes) *passes = h->passes;
     if (sweeps) *sweeps = h->sweeps;
     return MOR_OK;
@@ -736,6 +722,7 @@ int32_t mor_b200_pod_info(mor_pod_t h, int32_t* passes, int32_t* sweeps) {
 
 int32_t mor_b200_orthonormalize_dev(mor_mat_t A, int32_t* passes) {
     MOR_API_LOCK;
+    MOR_ROUTE_SOLO(mor_b200_orthonormalize_dev(A, passes));
     MOR_ARG(A != nullptr, "mor_b200_orthonormalize_dev: null matrix");
     MOR_TRY(require_ctx());
     MOR_ARG(A->n >= 1 && A->n <= 4096, "mor_b200_orthonormalize_dev: column count must be in 1..4096");

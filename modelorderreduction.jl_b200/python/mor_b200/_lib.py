@@ -48,6 +48,8 @@ SIGNATURES = {
     "mor_b200_trim": (_i32, []),
     "mor_b200_host_alloc": (_i32, [_u64, C.POINTER(_p)]),
     "mor_b200_host_free": (_i32, [_p]),
+    "mor_b200_init_multi": (_i32, [_i32]),
+    "mor_b200_multi_info": (_i32, [_pi32]),
     "mor_b200_comm_unique_id": (_i32, [_p]),
     "mor_b200_comm_init": (_i32, [_i32, _i32, _p]),
     "mor_b200_comm_info": (_i32, [_pi32, _pi32]),

@@ -28,6 +28,18 @@ def shard_rows(m_global: int, nranks: int, rank: int, align: int = 4) -> Tuple[i
     return row0, row1 - row0
 
 
+def init_multi(ngpus: int) -> None:
+    """Single-process multi-GPU mode: this process drives `ngpus` GPUs, the library shards the rows of every host
+    matrix handed to the host-pointer entry points (mor_b200_init_multi; MOR_B200_NGPUS does the same lazily)."""
+    _lib.check(_lib.load().mor_b200_init_multi(ngpus))
+
+
+def multi_info() -> int:
+    n = C.c_int32(0)
+    _lib.check(_lib.load().mor_b200_multi_info(C.byref(n)))
+    return n.value
+
+
 def init(device: int) -> None:
     _lib.check(_lib.load().mor_b200_init(device))
 

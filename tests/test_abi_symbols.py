@@ -23,6 +23,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in mor_b200.h but not exported"
 
 
+def test_product_library_exports_only_the_header_abi():
+    """nm -D: the extern "C" surface of libmor_b200.so is exactly include/mor_b200.h; the kernel test hooks
+    (mor_dbg_*) live in libmor_b200_test.so."""
+    import subprocess
+    libdir = os.path.join(ROOT, "modelorderreduction.jl_b200", "lib")
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(libdir, "libmor_b200.so")], capture_output=True, text=True, check=True).stdout
+    exported = sorted({line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith(("mor_b200_", "mor_dbg_"))})
+    assert exported == header_symbols()
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(libdir, "libmor_b200_test.so")], capture_output=True, text=True, check=True).stdout
+    assert any(line.endswith("mor_dbg_peaks") for line in out.splitlines())
+
+
 def test_bindings_cover_header():
     syms = header_symbols()
     assert sorted(_lib.SIGNATURES) == syms

@@ -23,3 +23,23 @@ def test_two_gpu_sharded_paths(gpu):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DEIM ok on 2 GPUs" in out.stdout
+
+
+def test_single_process_multi_gpu_mode(gpu):
+    """mor_b200_init_multi: one process, all visible GPUs (also meaningful with one: worker thread, staged ingest)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "single_process_multi_check.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "single-process multi-GPU check ok" in out.stdout
+
+
+def test_lazy_multi_gpu_start_from_environment(gpu):
+    """MOR_B200_NGPUS: the first call of an uninitialised process starts the multi-GPU mode."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    env = dict(os.environ, MOR_B200_NGPUS="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "single_process_multi_check.py")],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "single-process multi-GPU check ok on 2 GPU(s)" in out.stdout
