@@ -214,6 +214,92 @@ def workload_config(args, world):
     return cfg
 
 
+def single_process_leg(args, world, lib, s_multi, idx_control):
+    """Rank 0 alone, all `world` GPUs through mor_b200_init_multi: the drop-in a single Julia session gets
+    (reduce!(pod, SVD()) on the whole 16M x 1024 host matrix, deim_interpolation_indices on a 16M x 256 host basis).
+    The library shards the caller's matrix by rows, one worker thread per GPU."""
+    import numpy as np
+    from mor_b200 import _lib
+    from mor_b200 import dist as mdist
+    from mor_b200.device import DeviceMatrix, orthonormalize_dev
+    M, n, k = args.rows, N_COLS, K_MODES
+    mdist.init_multi(world)
+    out = {"ngpus": world, "api": "mor_b200_init_multi + mor_b200_pod_factor / mor_b200_pod_basis / mor_b200_deim_indices "
+                                  "(host pointers, ONE process, the library shards the rows)"}
+    need_gb = (M * n + M * k) * 8 / 1e9
+    if need_gb * 1.1 + 16 > mem_available_gb():
+        out["skipped"] = f"needs {need_gb:.0f} GB of host memory, {mem_available_gb():.0f} GB available"
+        lib.mor_b200_shutdown()
+        return out
+
+    def fill(ptr, kind, seed, param, iparam, rows, cols, chunk):
+        """column-major host matrix (ld = rows) from the device generator, chunk by chunk through GPU 0"""
+        for r0 in range(0, rows, chunk):
+            rc = min(chunk, rows - r0)
+            d = DeviceMatrix.alloc(rc, cols).synth(kind, seed=seed, global_row0=r0, param=param, iparam=iparam)
+            _lib.check(lib.mor_b200_mat_download(d.handle, C.c_void_p(ptr + r0 * 8), rows))
+            d.free()
+
+    S = np.empty(n); nS = C.c_int64(0)
+
+    def pod_e2e(xptr, uptr, steps, warmup):
+        def step():
+            h = C.c_void_p()
+            _lib.check(lib.mor_b200_pod_factor(xptr, M, n, M, _lib.MOR_SVD, k, 0, None, 0, C.byref(h), S.ctypes.data, C.byref(nS)))
+            _lib.check(lib.mor_b200_pod_basis(h, k, uptr, M, None, 0))
+            lib.mor_b200_pod_free(h)
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return (time.perf_counter() - t0) / steps * 1e3
+
+    Xh, Uh = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.mor_b200_host_alloc(M * n * 8, C.byref(Xh)))
+    _lib.check(lib.mor_b200_host_alloc(M * k * 8, C.byref(Uh)))
+    fill(Xh.value, _lib.SYNTH_GRADED, 3, 3.0, 0, M, n, 1 << 20)
+    ms = pod_e2e(Xh, Uh, args.e2e_steps, args.e2e_warmup)
+    out["pod_e2e"] = {"value": pod_flops(M, n, k) / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms,
+                      "h2d_bytes_per_step": M * n * 8, "d2h_bytes_per_step": M * k * 8 + n * 8, "host_memory": "pinned",
+                      "sigma_max_rel_diff_vs_one_process_per_gpu": float(np.max(np.abs(S - s_multi) / s_multi))}
+    if not args.no_pageable and need_gb * 2.1 + 16 < mem_available_gb():
+        Xp = np.empty(M * n, dtype=np.float64)
+        Up = np.empty(M * k, dtype=np.float64)
+        fill(Xp.ctypes.data, _lib.SYNTH_GRADED, 3, 3.0, 0, M, n, 1 << 20)
+        ms = pod_e2e(Xp.ctypes.data, Up.ctypes.data, 1, 0)
+        out["pod_e2e"]["pageable"] = {"value": pod_flops(M, n, k) / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms,
+                                      "host_memory": "pageable (numpy), staged through pinned rings by host copy threads",
+                                      "sigma_max_rel_diff": float(np.max(np.abs(S - s_multi) / s_multi))}
+        del Xp, Up
+    lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
+    lib.mor_b200_trim()
+    # DEIM: the Philox control basis (generated and orthonormalised on GPU 0, then held on the host)
+    Md, kd = args.deim_rows, DEIM_K
+    Bh = C.c_void_p()
+    _lib.check(lib.mor_b200_host_alloc(Md * kd * 8, C.byref(Bh)))
+    Bd = DeviceMatrix.alloc(Md, kd).synth(_lib.SYNTH_GAUSS, seed=5, global_row0=0, param=1.0 / math.sqrt(Md))
+    orthonormalize_dev(Bd)
+    _lib.check(lib.mor_b200_mat_download(Bd.handle, Bh, Md))
+    Bd.free()
+    lib.mor_b200_trim()
+    idx = np.empty(kd, dtype=np.int64)
+    for it in range(args.e2e_warmup + args.e2e_steps):
+        if it == args.e2e_warmup:
+            t0 = time.perf_counter()
+        _lib.check(lib.mor_b200_deim_indices(Bh, Md, kd, Md, idx.ctypes.data))
+    ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
+    t = _lib.last_timings()
+    out["deim_e2e"] = {"ms": ms, "h2d_bytes_per_step": Md * kd * 8, "device_ms_rank0": t["total"], "exchange": t["deim_exchange"],
+                       "distinct_indices": len(set(idx.tolist())),
+                       "same_indices_as_one_process_per_gpu": bool(np.array_equal(idx, idx_control)),
+                       "note": "the control basis is orthonormalised on GPU 0 here and row-sharded in the other run: "
+                               "the two bases agree to rounding only, so equal indices are expected, not guaranteed"}
+    lib.mor_b200_host_free(Bh)
+    _lib.check(lib.mor_b200_shutdown())
+    return out
+
+
 def deim_independent_check(torch, dist, bt, m_loc, row0, idx, world, steps, lib_values=None):
     """Full-size check of the chosen DEIM points by an independent code path (torch fp64: cuSOLVER LU solve +
     cuBLAS gemv on the aliased basis; none of the library's kernels): for every checked greedy step l the
@@ -297,6 +383,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         mdist.init_from_torch(local)
+        import datetime
+        # host-side group: the other ranks wait here while rank 0 runs the single-process multi-GPU leg
+        gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30))
     else:
         mdist.init(local)
     lib = _lib.load()
@@ -443,33 +532,56 @@ def run_ours(args):
                 e2e = {"value": None, "unit": "TFLOP/s", "skipped": "pinned host allocation failed on at least one rank"}
         elif world > 1:
             all_ranks_ok(False)                 # keep the collective sequence identical on every rank
-        if e2e is None:
-            _lib.check(lib.mor_b200_mat_download(X.handle, Xh, max(m_loc, 1)))
-            X.free(); U.free()
-            S = np.empty(n); nS = C.c_int64(0)
+        S = np.empty(n); nS = C.c_int64(0)
 
+        def e2e_run(xptr, uptr, steps, warmup):
             def e2e_step():
                 h = C.c_void_p()
-                _lib.check(lib.mor_b200_pod_factor(Xh, m_loc, n, max(m_loc, 1), _lib.MOR_SVD,
+                _lib.check(lib.mor_b200_pod_factor(xptr, m_loc, n, max(m_loc, 1), _lib.MOR_SVD,
                                                    k, 0, None, 0, C.byref(h), S.ctypes.data, C.byref(nS)))
-                _lib.check(lib.mor_b200_pod_basis(h, k, Uh, max(m_loc, 1), None, 0))
+                _lib.check(lib.mor_b200_pod_basis(h, k, uptr, max(m_loc, 1), None, 0))
                 lib.mor_b200_pod_free(h)
-
-            for _ in range(args.e2e_warmup):
+            for _ in range(warmup):
                 e2e_step()
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
+            for _ in range(steps):
                 e2e_step()
             barrier()
-            e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps * 1e3)
+            return max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+
+        if e2e is None:
+            _lib.check(lib.mor_b200_mat_download(X.handle, Xh, max(m_loc, 1)))
+            X.free(); U.free()
+            e2e_ms = e2e_run(Xh, Uh, args.e2e_steps, args.e2e_warmup)
             e2e = {"value": pod_flops(M, n, k) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": int(sum_over_ranks(m_loc * n * 8)),
                    "d2h_bytes_per_step": int(sum_over_ranks(m_loc * k * 8) + n * 8),
                    "steps": args.e2e_steps, "warmup": args.e2e_warmup, "host_memory": "pinned",
                    "api": "mor_b200_pod_factor + mor_b200_pod_basis (host pointers)"}
+            s_pinned = S.copy()
             lib.mor_b200_host_free(Xh); lib.mor_b200_host_free(Uh)
             lib.mor_b200_trim()      # drop the parked 137 GB ingest copy before the next phases
+            # the same call on PAGEABLE host memory (what a Julia Matrix is): numpy buffers, the library stages them
+            # through its pinned ring (csrc/ingest.cpp).  The matrix is regenerated on the device and downloaded.
+            if not args.no_pageable:
+                try:
+                    Xp = np.empty(max(m_loc, 1) * n, dtype=np.float64)
+                    Up = np.empty(max(m_loc, 1) * k, dtype=np.float64)
+                    X = DeviceMatrix.alloc(m_loc, n).synth(_lib.SYNTH_GRADED, seed=3, global_row0=row0, param=3.0)
+                    _lib.check(lib.mor_b200_mat_download(X.handle, Xp.ctypes.data, max(m_loc, 1)))
+                    X.free()
+                    pg_ms = e2e_run(Xp.ctypes.data, Up.ctypes.data, 1, 0)
+                    e2e["pageable"] = {"value": pod_flops(M, n, k) / (pg_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": pg_ms,
+                                       "steps": 1, "warmup": 0, "host_memory": "pageable (numpy / malloc; staged through the "
+                                       "library's pinned ring by host copy threads)",
+                                       "same_spectrum_as_pinned": bool(np.array_equal(S, s_pinned)),
+                                       "ingest_threads_per_gpu": int(os.environ.get("MOR_B200_INGEST_THREADS", "0")) or
+                                       max(1, min(8, (os.cpu_count() or 1)))}
+                    del Xp, Up
+                    lib.mor_b200_trim()
+                except MemoryError as ex:
+                    e2e["pageable"] = {"skipped": repr(ex)}
     X.free(); U.free()
 
     # ---- known-answer run at FULL size: X = H_u [S V'; 0] (exact singular values / left vectors) -------
@@ -745,8 +857,26 @@ def run_ours(args):
                          "inside the kernel); update = per-panel coefficient and inverse-update launches",
             "e2e": deim_e2e}
     B.free()
+    single = None
     if world > 1:
         dist.barrier()
+        if not args.no_single_process and not args.no_e2e:
+            # every rank lets go of its GPU; rank 0 then drives all `world` GPUs from ONE process (mor_b200_init_multi)
+            lib.mor_b200_trim()
+            _lib.check(lib.mor_b200_set_stream(None))
+            _lib.check(lib.mor_b200_shutdown())
+            torch.cuda.empty_cache()
+            dist.barrier(group=gloo)
+            if rank == 0:
+                try:
+                    single = single_process_leg(args, world, lib, info["s"], idx_c)
+                except Exception as ex:         # never lose the bench line over the extra leg
+                    single = {"error": repr(ex)}
+                    try:
+                        lib.mor_b200_shutdown()
+                    except Exception:
+                        pass
+            dist.barrier(group=gloo)
         dist.destroy_process_group()
 
     if rank != 0:
@@ -783,7 +913,8 @@ def run_ours(args):
                          "traffic": TRAFFIC_RATIO_GRAM * 8.0 * m_loc * n,
                          "traffic_note": f"ncu-measured {TRAFFIC_RATIO_GRAM:.3f} x (8 m n) bytes at 2M rows, scaled to this launch's rows",
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
-            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "cpu_baseline": cpu}
+            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "single_process": single,
+            "cpu_baseline": cpu}
     emit(line)
 
 
@@ -813,6 +944,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory e2e leg")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the single-process multi-GPU leg on rank 0")
     ap.add_argument("--no-rsvd", action="store_true")
     ap.add_argument("--no-kat", action="store_true")
     ap.add_argument("--rsvd-rows-per-gpu", type=int, default=8 * 2**20)

@@ -268,11 +268,19 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     tm.core.start();
     DebugLaps dbg("factor_tall: core SVD");
     const bool accumulate_v = replicated || n < 64;
+    // One pass, tall side: only V and S are needed (U = X V S^-1), so the Jacobi runs on the columns of R' -- the
+    // rotated columns converge to v_j s_j directly (no accumulation, no inv(R), no n^3 products afterwards), and
+    // one-sided Jacobi on the transposed triangular factor converges at least as fast (Veselic-Hari, Drmac-Veselic).
+    const bool on_transpose = single_pass && !accumulate_v;
     MOR_TRY(A.alloc(nn));
     MOR_CUDA(cudaMemcpyAsync(A.p, Rtot.p, nn, cudaMemcpyDeviceToDevice, st));
     // rows of R that belong to all-zero snapshot columns carry no energy
     MOR_TRY(small_zero_rows(A.as<double>(), n, n, n, D1.as<double>()));
-    if (!accumulate_v) MOR_CUDA(cudaMemcpyAsync(Rtot.p, A.p, nn, cudaMemcpyDeviceToDevice, st));  // keep R (deflated)
+    if (!accumulate_v && !on_transpose) MOR_CUDA(cudaMemcpyAsync(Rtot.p, A.p, nn, cudaMemcpyDeviceToDevice, st));  // keep R (deflated)
+    if (on_transpose) {
+        MOR_TRY(transpose(A.as<double>(), n, n, n, G.as<double>(), n));
+        MOR_CUDA(cudaMemcpyAsync(A.p, G.p, nn, cudaMemcpyDeviceToDevice, st));
+    }
     std::vector<int> order;
     int sweeps = 0;
     dbg.lap("copy R / deflate");
@@ -293,7 +301,7 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     }
     for (int j = 0; j < n; ++j) {
         is[j] = h->sigma[j] > 0.0 ? 1.0 / h->sigma[j] : 0.0;
-        ib[j] = is[j] * iv[j];
+        ib[j] = on_transpose ? is[j] * is[j] : is[j] * iv[j];
     }
     MOR_TRY(upload_vec(is, inv_sigma));
     MOR_TRY(upload_vec(iv, inv_vn));
@@ -303,7 +311,11 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     if (accumulate_v) {
         MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_vn.as<double>(), h->Vs.as<double>(), n));
     }
-    if (single_pass && accumulate_v) {
+    if (on_transpose) {
+        // columns of A are v_j s_j:  V = A S^-1,  M = V S^-1 = A S^-2
+        MOR_TRY(gather_cols(A.as<double>(), n, n, n, perm.as<int>(), inv_sigma.as<double>(), h->Vs.as<double>(), n));
+        MOR_TRY(gather_cols(A.as<double>(), n, n, n, perm.as<int>(), inv_both.as<double>(), h->M.as<double>(), n));
+    } else if (single_pass && accumulate_v) {
         // T = U S V'  =>  U = T V S^-1
         MOR_TRY(gather_cols(V.as<double>(), n, n, n, perm.as<int>(), inv_both.as<double>(), h->M.as<double>(), n));
     } else {

@@ -13,6 +13,14 @@
 # Untouched and still executed in Julia: POD constructors + errorhandle (ErrorHandle.jl:1-18),
 # determine_truncation (POD.jl:121-132, quirks preserved), the symbolic deim(sys, ...) (deim.jl:207-265).
 #
+# Outside the library's limits the shim DEFERS to the reference's own method (`invoke`), it never errors where the
+# reference would succeed: small dimension > 4096, more than 1024 DEIM basis vectors, backend keyword arguments the
+# library does not understand (Types.jl:61-95 forwards `alg.kwargs` verbatim at POD.jl:157,196), non-convergence.
+# `defers(...)` below is that rule; python/mor_b200/pod.py mirrors it (DeferToReference).
+#
+# Multi-GPU from ONE Julia session: `MORB200.init_multi(8)` or `MOR_B200_NGPUS=8` in the environment -- the library
+# shards the rows of the snapshot matrix over the GPUs itself (include/mor_b200.h, mor_b200_init_multi).
+#
 # NOTE: Julia is not installed in the build image, so this file is exercised only through its
 # 1:1 ctypes mirror (python/mor_b200/*.py, which the GPU parity tests drive).
 module MORB200
@@ -30,9 +38,27 @@ const F64VoV = Vector{Vector{Float64}}
 
 last_error() = unsafe_string(ccall((:mor_b200_last_error, LIB), Cstring, ()))
 
+const MAX_SMALL_DIM = 4096      # include/mor_b200.h: the small side of the snapshot matrix
+const MAX_DEIM_COLS = 1024
+
+"`true` when this call must run the reference's own Julia method instead of the library."
+function defers(m::Integer, n::Integer, kwargs)
+    min(m, n) > MAX_SMALL_DIM && return true
+    for key in keys(kwargs)
+        key === :full && kwargs[key] == false && continue          # thin SVD is what the library computes
+        key === :alg && continue                                    # LAPACK driver choice: same result
+        key in (:initvec, :tolconv, :maxiter) && continue           # TSVD.jl's Lanczos knobs: exact top-k is returned
+        return true
+    end
+    return false
+end
+snapsize(X::StridedMatrix) = size(X)
+snapsize(V::Vector{<:Vector}) = (length(V[1]), length(V))
+
 function check(st::Integer)
     st == 0 && return nothing
     msg = last_error()
+    st == 5 && error("libmor_b200 status 5: $msg")               # caught by factor_or_nothing -> reference method
     (st == 1 || st == 2) && throw(ArgumentError(msg))          # bad argument / non-finite input
     st == 6 && throw(SingularException(0))                     # deim.jl:21 `\` on a singular P'U
     st == 4 && throw(OutOfMemoryError())
@@ -42,6 +68,22 @@ end
 "Bind this process to a GPU (one process per GPU); optional, device 0 is bound lazily."
 init(device::Integer = parse(Int, get(ENV, "MOR_B200_DEVICE", "0"))) =
     check(ccall((:mor_b200_init, LIB), Cint, (Cint,), device))
+
+"ONE Julia process drives `ngpus` GPUs: the library shards the rows of every host matrix (also: MOR_B200_NGPUS)."
+init_multi(ngpus::Integer = parse(Int, get(ENV, "MOR_B200_NGPUS", "1"))) =
+    check(ccall((:mor_b200_init_multi, LIB), Cint, (Cint,), ngpus))
+
+"(margins, values) of the last `deim_interpolation_indices` call: relative gap to the runner-up and winning residual
+of every greedy step (mor_b200_deim_last_margins)."
+function deim_last_margins()
+    n = Ref{Int64}(0)
+    check(ccall((:mor_b200_deim_last_margins, LIB), Cint,
+        (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}), C_NULL, C_NULL, 0, n, C_NULL, C_NULL))
+    margins, values = zeros(n[]), zeros(n[])
+    check(ccall((:mor_b200_deim_last_margins, LIB), Cint,
+        (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}), margins, values, n[], C_NULL, C_NULL, C_NULL))
+    return margins, values
+end
 
 "Multi-GPU: rank 0 calls `unique_id()`, the host runtime (Distributed / MPI) broadcasts the 128 bytes,
 every rank calls `comm_init(rank, nranks, id)`; snapshot ROWS are then sharded over the ranks in rank order."
@@ -72,7 +114,7 @@ omega_ptr(Ω::Matrix{Float64}) = pointer(Ω)
 function factor(X::F64Mat, method::Cint, k::Integer, p::Integer = 0; omega = nothing, seed::Integer = 0)
     stride(X, 1) == 1 || (X = Matrix(X))
     m, n = size(X)
-    s = Vector{Float64}(undef, min(m, n))
+    s = Vector{Float64}(undef, n)        # capacity min(M_global, n) <= n, also when this process holds a row shard
     nS = Ref{Int64}(0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve X omega begin
@@ -88,7 +130,7 @@ function factor(V::F64VoV, method::Cint, k::Integer, p::Integer = 0; omega = not
     n, m = length(V), length(V[1])
     all(v -> length(v) == m, V) || throw(DimensionMismatch("snapshots of unequal length"))
     cols = [pointer(v) for v in V]
-    s = Vector{Float64}(undef, min(m, n))
+    s = Vector{Float64}(undef, n)
     nS = Ref{Int64}(0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve V cols omega begin
@@ -112,9 +154,23 @@ release!(f::Factor) = finalize(f)
 
 const Snaps = Union{F64Mat, F64VoV}
 
+struct NotConverged <: Exception end
+function factor_or_nothing(args...; kw...)
+    try
+        return factor(args...; kw...)
+    catch e
+        # status 5 (CholeskyQR passes / Jacobi sweeps exhausted): the reference's LAPACK path takes over
+        e isa ErrorException && occursin("status 5", e.msg) || rethrow()
+        @warn "libmor_b200 did not converge; running the reference method" exception = e
+        return nothing
+    end
+end
+
 # POD.jl:156-166
 function reduce!(pod::POD{S, Float64}, alg::SVD)::Nothing where {S <: Snaps}
-    f = factor(pod.snapshots, MOR_SVD, pod.max_nmodes)
+    defers(snapsize(pod.snapshots)..., alg.kwargs) && return invoke(reduce!, Tuple{POD, SVD}, pod, alg)
+    f = factor_or_nothing(pod.snapshots, MOR_SVD, pod.max_nmodes)
+    f === nothing && return invoke(reduce!, Tuple{POD, SVD}, pod, alg)
     s = f.s                                                           # full spectrum, POD.jl:164
     pod.nmodes, pod.renergy = determine_truncation(s, pod.min_nmodes, pod.max_nmodes, pod.min_renergy)
     pod.rbasis = basis(f, pod.nmodes)                                 # POD.jl:163
@@ -126,7 +182,9 @@ end
 # POD.jl:195-202 -- TSVD.jl's Lanczos knobs (initvec, tolconv, maxiter) are accepted and ignored:
 # the library returns the exact top-k triplets the iteration converges to.
 function reduce!(pod::POD{S, Float64}, alg::TSVD)::Nothing where {S <: Snaps}
-    f = factor(pod.snapshots, MOR_TSVD, pod.nmodes)
+    defers(snapsize(pod.snapshots)..., alg.kwargs) && return invoke(reduce!, Tuple{POD, TSVD}, pod, alg)
+    f = factor_or_nothing(pod.snapshots, MOR_TSVD, pod.nmodes)
+    f === nothing && return invoke(reduce!, Tuple{POD, TSVD}, pod, alg)
     s = f.s
     n_max = min(f.m, f.n)                                             # POD.jl:197
     pod.renergy = sum(s) / (sum(s) + (n_max - pod.nmodes) * s[end])   # POD.jl:198
@@ -141,7 +199,9 @@ end
 const rsvd_seed = Ref{UInt64}(0)
 const rsvd_omega = Ref{Union{Nothing, Matrix{Float64}}}(nothing)
 function reduce!(pod::POD{S, Float64}, alg::RSVD)::Nothing where {S <: Snaps}
-    f = factor(pod.snapshots, MOR_RSVD, pod.nmodes, alg.p; omega = rsvd_omega[], seed = rsvd_seed[])
+    defers(snapsize(pod.snapshots)..., NamedTuple()) && return invoke(reduce!, Tuple{POD, RSVD}, pod, alg)
+    f = factor_or_nothing(pod.snapshots, MOR_RSVD, pod.nmodes, alg.p; omega = rsvd_omega[], seed = rsvd_seed[])
+    f === nothing && return invoke(reduce!, Tuple{POD, RSVD}, pod, alg)
     s = f.s
     n_max = min(f.m, f.n)                                             # POD.jl:233
     pod.renergy = sum(s) / (sum(s) + (n_max - pod.nmodes) * s[end])   # POD.jl:234
@@ -153,6 +213,7 @@ end
 
 # deim.jl:9-28
 function deim_interpolation_indices(B::F64Mat)::Vector{Int}
+    size(B, 2) > MAX_DEIM_COLS && return invoke(deim_interpolation_indices, Tuple{AbstractMatrix}, B)
     stride(B, 1) == 1 || (B = Matrix(B))
     m, k = size(B)
     idx = Vector{Int64}(undef, k)

@@ -14,6 +14,9 @@ def deim_interpolation_indices(basis: np.ndarray) -> np.ndarray:
     if basis.dtype != np.float64:
         raise TypeError("the B200 path handles Float64 (the shim defers other types to the reference)")
     m, k = basis.shape
+    if k > 1024:
+        from .pod import DeferToReference
+        raise DeferToReference(f"{k} basis vectors > 1024 (the Julia shim runs the reference's deim_interpolation_indices)")
     strided_ok = (m <= 1 or basis.strides[0] == 8) and (
         k <= 1 or (basis.strides[1] % 8 == 0 and basis.strides[1] // 8 >= m))
     B = basis if strided_ok else np.asfortranarray(basis)

@@ -24,6 +24,37 @@ from . import _lib
 
 Snapshots = Union[np.ndarray, Sequence[np.ndarray]]
 
+MAX_SMALL_DIM = 4096       # include/mor_b200.h: the small side of the snapshot matrix
+_SVD_KWARGS_OK = {"alg"}                              # LAPACK driver choice: same result
+_TSVD_KWARGS_OK = {"initvec", "tolconv", "maxiter"}   # TSVD.jl's Lanczos knobs: the exact top-k is returned
+
+
+class DeferToReference(NotImplementedError):
+    """The call is outside what libmor_b200 handles; the Julia shim `invoke`s the reference's own method here
+    (julia/MORB200.jl: `defers`).  This Python mirror has no reference implementation to fall back to, so it
+    says so instead of guessing."""
+
+
+def defer_reason(snaps: Snapshots, alg) -> Optional[str]:
+    """The shim's rule (MORB200.jl `defers`): why this call must run the reference's own method, or None.
+    /root/reference/src/Types.jl:61-95 forwards `alg.kwargs` verbatim (POD.jl:157,196); ErrorHandle.jl:1-7 accepts
+    any size."""
+    m, n = (len(snaps[0]), len(snaps)) if _is_vov(snaps) else snaps.shape
+    if min(m, n) > MAX_SMALL_DIM:
+        return f"small dimension {min(m, n)} > {MAX_SMALL_DIM}"
+    kw = getattr(alg, "kwargs", {}) or {}
+    for key, val in kw.items():
+        if key == "full" and val is False:
+            continue
+        if isinstance(alg, SVD) and key in _SVD_KWARGS_OK:
+            continue
+        if isinstance(alg, TSVD) and key in _TSVD_KWARGS_OK:
+            continue
+        return f"backend keyword argument {key}={val!r} is not understood by libmor_b200"
+    if not _is_vov(snaps) and snaps.dtype != np.float64:
+        return f"element type {snaps.dtype} (the library is Float64 only)"
+    return None
+
 
 # ---- backend tags (Types.jl:61-124) ---------------------------------------------------------
 class SVD:
@@ -162,7 +193,7 @@ def _factor(snaps: Snapshots, method: int, k: int, p: int = 0,
         for c in cols:
             if c.shape != (m,):
                 raise ValueError("all snapshots must have the same length")
-        cap = min(m_global if m_global is not None else m, n)
+        cap = n                                     # min(M_global, n) <= n, also for a row shard
         s = np.empty(cap, dtype=np.float64)
         ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in cols])
         st = lib.mor_b200_pod_factor_cols(ptrs, m, n, method, k, p, om_ptr, seed,
@@ -177,7 +208,7 @@ def _factor(snaps: Snapshots, method: int, k: int, p: int = 0,
         if not strided_ok:
             X = np.asfortranarray(X)
         ldx = X.strides[1] // 8 if n > 1 else max(m, 1)
-        cap = min(m_global if m_global is not None else m, n)
+        cap = n
         s = np.empty(cap, dtype=np.float64)
         st = lib.mor_b200_pod_factor(X.ctypes.data, m, n, max(ldx, 1), method, k, p, om_ptr, seed,
                                      C.byref(handle), s.ctypes.data, C.byref(nS))
@@ -189,6 +220,10 @@ def reduce(pod: POD, alg, *, omega: Optional[np.ndarray] = None, seed: int = 0) 
     """`reduce!(pod, alg)` -- mutates `pod`, returns None (POD.jl:156-166,195-202,231-238).
     `omega`/`seed` exist only for RSVD: the reference draws Omega from Julia's global RNG;
     here it is either supplied (shared with the oracle) or drawn by the library from `seed`."""
+    if isinstance(alg, (SVD, TSVD, RSVD)):
+        why = defer_reason(pod.snapshots, alg)
+        if why is not None:
+            raise DeferToReference(why)
     if isinstance(alg, SVD):
         f = _factor(pod.snapshots, _lib.MOR_SVD, pod.max_nmodes)
         try:

@@ -1,5 +1,7 @@
 """Host-side mirror (mor_b200) logic that runs without a GPU: constructors, assertions,
 truncation quirks, shard partitioning -- checked against the oracle / reference behaviour."""
+import os
+
 import numpy as np
 import pytest
 
@@ -65,3 +67,29 @@ def test_reduce_rejects_unknown_backend():
     pod = mor_b200.POD(np.ones((4, 2)), 1)
     with pytest.raises(TypeError):
         mor_b200.reduce(pod, object())
+
+
+def test_shim_defers_outside_the_library_limits():
+    """MORB200.jl `defers` / pod.py `defer_reason`: the shim never errors where the reference would succeed
+    (Types.jl:61-95 kwargs forwarded at POD.jl:157,196; ErrorHandle.jl accepts any size) -- it runs the reference's own
+    method instead.  The Python mirror has no reference to fall back to and raises DeferToReference BEFORE any
+    library call (so this runs without a GPU)."""
+    import mor_b200
+    X = np.zeros((5000, 4200))
+    assert "small dimension" in mor_b200.defer_reason(X, mor_b200.SVD())
+    with pytest.raises(mor_b200.DeferToReference):
+        mor_b200.reduce(mor_b200.POD(X, 3), mor_b200.SVD())
+    Y = np.ones((10, 4))
+    assert mor_b200.defer_reason(Y, mor_b200.SVD()) is None
+    assert mor_b200.defer_reason(Y, mor_b200.SVD(full=False)) is None
+    assert mor_b200.defer_reason(Y, mor_b200.SVD(alg="QRIteration")) is None
+    assert "full" in mor_b200.defer_reason(Y, mor_b200.SVD(full=True))
+    assert mor_b200.defer_reason(Y, mor_b200.TSVD(tolconv=1e-12, maxiter=50)) is None
+    assert "stepsize" in mor_b200.defer_reason(Y, mor_b200.TSVD(stepsize=3))
+    assert "float32" in mor_b200.defer_reason(Y.astype(np.float32), mor_b200.SVD())
+    with pytest.raises(mor_b200.DeferToReference):
+        mor_b200.deim_interpolation_indices(np.zeros((2000, 1025), order="F"))
+    shim = open(os.path.join(os.path.dirname(__file__), "..", "modelorderreduction.jl_b200", "julia", "MORB200.jl")).read()
+    for needle in ("invoke(reduce!, Tuple{POD, SVD}", "invoke(reduce!, Tuple{POD, TSVD}", "invoke(reduce!, Tuple{POD, RSVD}",
+                   "invoke(deim_interpolation_indices", "mor_b200_init_multi", "Vector{Float64}(undef, n)"):
+        assert needle in shim
