@@ -558,7 +558,18 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
     const char* ch_env = getenv("MOR_B200_INGEST_CHUNK_ROWS");  // test hook: force small chunks
     const bool pipelined = !cols && method != MOR_RSVD && m >= n && n <= 4096 &&
                            (ch_env != nullptr || (size_t)m * n >= (size_t(1) << 24));
-    std::vector<cudaEvent_t> events;
+    // On every exit path (errors included): nothing may still be reading the caller's buffer or writing into dX
+    // when they go away, and the events are released.
+    struct IngestGuard {
+        Ctx& cx;
+        std::vector<cudaEvent_t> events;
+        ~IngestGuard() {
+            if (cx.copy_stream) cudaStreamSynchronize(cx.copy_stream);
+            cudaStreamSynchronize(cx.stream);
+            for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+        }
+    } guard{cx, {}};
+    std::vector<cudaEvent_t>& events = guard.events;
     if (m > 0 && pipelined) {
         if (!cx.copy_stream) MOR_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
         MOR_TRY(Gacc.alloc(sizeof(double) * (size_t)n * n));
@@ -606,8 +617,6 @@ static int32_t factor_from_host(const double* X, const double* const* cols, int6
                                    S_out, nS, tm, (m > 0 && pipelined) ? Gacc.as<double>() : nullptr);
     tm.total.stop();
     cudaStreamSynchronize(cx.stream);
-    if (cx.copy_stream) cudaStreamSynchronize(cx.copy_stream);
-    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     tm.collect();
     return st;
 }

@@ -81,8 +81,9 @@ class DeviceMatrix:
 class DeviceFactor:
     """mor_pod_t obtained from a device-resident snapshot matrix."""
 
-    def __init__(self, handle, s: np.ndarray):
+    def __init__(self, handle, s: np.ndarray, keep=None):
         self.handle, self.s = handle, s
+        self._keep = keep      # the handle may borrow X's device memory (include/mor_b200.h): keep it alive
 
     def basis(self, k: int, out: DeviceMatrix) -> DeviceMatrix:
         _lib.check(_lib.load().mor_b200_pod_basis_dev(self.handle, k, out.handle))
@@ -120,7 +121,7 @@ def pod_factor_dev(X: DeviceMatrix, method: int, k: int, p: int = 0,
     _lib.check(_lib.load().mor_b200_pod_factor_dev(
         X.handle, method, k, p, omega.handle if omega is not None else None, seed, flags,
         C.byref(h), s.ctypes.data, C.byref(nS)))
-    return DeviceFactor(h, s[:nS.value].copy())
+    return DeviceFactor(h, s[:nS.value].copy(), keep=X)
 
 
 def orthonormalize_dev(A: DeviceMatrix) -> int:
