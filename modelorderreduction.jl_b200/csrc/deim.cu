@@ -17,6 +17,7 @@
 //
 // The streaming path (MOR_B200_DEIM_BLOCK=0, k <= 16, or a basis the bulk copies cannot take) is the reference's
 // own access pattern: one pass over columns 1..l per step, coefficients from the bordered LU of the k x k block.
+#include <algorithm>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
@@ -148,7 +149,8 @@ struct TailArgs {
     // rows gathered at the local winner
     const double* U;                  // basis shard
     int64_t ldU;
-    int k, kcols;                     // record carries U[idx, 0..kcols), zeros beyond (columns still on the PCIe link)
+    int k;                            // columns of the basis
+    int krec;                         // the record carries U[idx, 0..krec): k on the streaming path, 0 on the blocked one
     const double* Pn;                 // residual panel (blocked path) or nullptr
     int64_t ldn;
     int bw;
@@ -164,7 +166,7 @@ struct TailArgs {
     unsigned tag;                     // this step's number (never 0)
     int mode;                         // 0: fused (local + peer exchange + global), 1: local part only (NCCL follows)
     // global part
-    double* W;                        // k x k rows of the basis at the chosen points (row-major, stride k)
+    double* W;                        // streaming path: k x k rows of the basis at the chosen points (row-major)
     long long* idx_out;
     double* margins;
     double* values;                   // winning residual of every step
@@ -241,7 +243,7 @@ __device__ __forceinline__ void deim_pick_winner(const TailArgs& a, TailSmem& ts
 
 // Last part of the tail: `wrec` (shared memory) is the winner's record, ts.st the small LU states.
 __device__ void deim_tail_finish(const TailArgs& a, const double* wrec, TailSmem& ts) {
-    const int tid = threadIdx.x, k = a.k;
+    const int tid = threadIdx.x, k = a.krec;
     for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = wrec[2 + jx];
     if (!a.blocked) return;
     constexpr int BB = DEIM_BLOCK * DEIM_BLOCK, SS = DEIM_SUB * DEIM_SUB;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void deim_prefetch_state(const TailArgs& a, TailSmem&
 
 // The tail, entered by every thread of the LAST CTA of a step kernel.  sbuf: >= rec doubles of shared memory.
 __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2, TailSmem& ts) {
-    const int tid = threadIdx.x, k = a.k, rec = a.rec;
+    const int tid = threadIdx.x, k = a.krec, rec = a.rec;
     unsigned long long t0 = 0;
     if (tid == 0) {
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -307,7 +309,7 @@ __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long
     // (b) the record: [value, bits(global index), U[idx, 0..k), panel row (16), sub-panel row (4), runner-up]
     const long long g = ts.widx;
     for (int jx = tid; jx < k; jx += DEIM_THREADS)
-        sbuf[2 + jx] = (g == MOR_IDX_NONE || jx >= a.kcols) ? 0.0 : __ldcg(&a.U[(g - a.row_offset) + (int64_t)jx * a.ldU]);
+        sbuf[2 + jx] = g == MOR_IDX_NONE ? 0.0 : __ldcg(&a.U[(g - a.row_offset) + (int64_t)jx * a.ldU]);
     if (a.blocked) {
         if (tid < DEIM_BLOCK)
             sbuf[2 + k + tid] = (g == MOR_IDX_NONE || tid >= a.bw || a.Pn == nullptr) ? 0.0 : __ldcg(&a.Pn[(g - a.row_offset) + (int64_t)tid * a.ldn]);
@@ -695,16 +697,19 @@ deim_update_kernel(const double* __restrict__ Wm, double* __restrict__ Uf, doubl
 }
 
 // ---- blocked path: A = inv(P'U) kept explicitly, extended once per panel ----------------------------------------
-// Pipelined host ingest: the basis arrives 16 columns at a time, so the rows of the points chosen so far cannot be
-// gathered beyond the columns that have landed.  At the panel boundary l0:
-//   W12[t][q] = U[idx[t], l0 + q], t < l0   (zero for rows of other ranks; all-reduced by the host)
-__global__ void __launch_bounds__(128)
-deim_gather_block_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset,
-                         const long long* __restrict__ idx, int l0, int bw, double* __restrict__ W12) {
-    const int t = blockIdx.x * 8 + threadIdx.x / DEIM_BLOCK, q = threadIdx.x % DEIM_BLOCK;
-    if (t >= l0) return;
+// The k x k block P'U is never formed on this path.  At a panel boundary two pieces of it are fetched from the
+// basis (each rank contributes the rows it owns, zeros elsewhere; the host all-reduces them when there are several):
+//   W21[c][t] = U[idx[l0 + c], t],       t < l0              (rows of the panel's new points, earlier columns)
+//   W12[t][q] = U[idx[t], l1 + q],       t < l1 = l0 + bw    (rows of all points so far, the next panel's columns)
+// out[(t - t0) * ldo + (c - c0)] = U[idx[t], c] for t in [t0, t1), c in [c0, c0 + nc)
+__global__ void __launch_bounds__(256)
+deim_gather_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset, const long long* __restrict__ idx,
+                   int t0, int t1, int c0, int nc, double* __restrict__ out, int ldo) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int t = t0 + e / nc, c = e % nc;
+    if (t >= t1) return;
     const long long loc = idx[t] - 1 - row_offset;
-    W12[t * DEIM_BLOCK + q] = (loc >= 0 && loc < m && q < bw) ? U[loc + (int64_t)(l0 + q) * ld] : 0.0;
+    out[(size_t)(t - t0) * ldo + c] = (loc >= 0 && loc < m) ? U[loc + (int64_t)(c0 + c) * ld] : 0.0;
 }
 
 // Coefficients of the panel that starts at column l0:  C = A[0:l0, 0:l0] * W12  (column q of C solves
@@ -766,11 +771,11 @@ deim_sinv_kernel(const double* __restrict__ bst, int bw, int k, int l0, double* 
     if (a < bw && b < bw) A[(size_t)(l0 + a) * k + l0 + b] = s;
 }
 
-// Panel end, step 2: F = Sinv * (W21 * A11)  (bw x l0), W21 = W[l0:l0+bw, 0:l0]; also A21 = -F.
+// Panel end, step 2: F = Sinv * (W21 * A11)  (bw x l0), W21 (bw x l0, row-major, stride l0) gathered from the basis; also A21 = -F.
 // One CTA per 16 columns j of A11: thread (ts, jj) accumulates rows t = ts (mod 16) of all 16 dot products of its
 // column (A[t][j] is read once, coalesced over jj), the 16 slices are summed through shared memory.
 __global__ void __launch_bounds__(256)
-deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W, int k, int l0, int bw,
+deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W21, int k, int l0, int bw,
                   const double* __restrict__ Sinv, double* __restrict__ F) {
     __shared__ double part[DEIM_BLOCK][DEIM_BLOCK][DEIM_BLOCK + 1];   // [slice][c][jj]
     __shared__ double e[DEIM_BLOCK][DEIM_BLOCK + 1], sinv[DEIM_BLOCK * DEIM_BLOCK];
@@ -783,7 +788,7 @@ deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W, int k, i
         for (int t = ts; t < l0; t += DEIM_BLOCK) {
             const double av = __ldcg(&A[(size_t)t * k + j]);
 #pragma unroll
-            for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = fma(c < bw ? __ldcg(&W[(size_t)(l0 + c) * k + t]) : 0.0, av, acc[c]);
+            for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = fma(c < bw ? __ldcg(&W21[(size_t)c * l0 + t]) : 0.0, av, acc[c]);
         }
 #pragma unroll
     for (int c = 0; c < DEIM_BLOCK; ++c) part[ts][c][jj] = acc[c];
@@ -885,40 +890,51 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     const bool fused = cx.nranks == 1 || cx.peers_ok;
 
     const size_t kk = (size_t)k * k;
-    // gathered record: value, index, basis row, [panel row (16), sub-panel row (4)], runner-up
-    const int rec = (int)k + 3 + (blocked ? DEIM_BLOCK + DEIM_SUB : 0);
+    // exchanged record: value, index, then -- streaming path: the winner's row of the basis (k); blocked path: its rows
+    // of the panel (16) and of the sub-panel (4) -- then the runner-up value
+    const int krec = blocked ? 0 : (int)k;
+    const int rec = krec + 3 + (blocked ? DEIM_BLOCK + DEIM_SUB : 0);
     DevBuf state, cands;
-    // state: W (k*k); blocked: A (k*k), F (16 k), C12 (16 k), W12 (16 k), packed Cp, Sinv, bst, sst, Dsub;
-    //        streaming: Uf, L, Z, Zt (k*k each), c (k); both: margins (k), idx (k int64), status
+    // state: blocked: A (k*k), F (16 k), C12 (16 k), gathered W21 | W12 (32 k), packed Cp, Sinv, bst, sst, Dsub;
+    //        streaming: W, Uf, L, Z, Zt (k*k each), c (k); both: margins, values (k), idx (k int64), status
     const size_t cp_doubles = (size_t)((k + DEIM_BLOCK - 1) / DEIM_BLOCK) * DEIM_BLOCK * 20;
     const size_t small_doubles = DEIM_BLOCK * DEIM_BLOCK + BST_DOUBLES + SST_DOUBLES + DEIM_BLOCK * DEIM_SUB;
-    const size_t ndoubles = kk + (blocked ? kk + 3 * (size_t)k * DEIM_BLOCK + cp_doubles + small_doubles : 4 * kk + (size_t)k) + 2 * (size_t)k;
+    // every piece starts on a 128-byte boundary (the panel kernel fetches the packed coefficients with bulk copies)
+    auto r16 = [](size_t nd) { return (nd + 15) & ~size_t(15); };
+    const size_t kb16 = r16((size_t)k * DEIM_BLOCK);
+    const size_t ndoubles = (blocked ? r16(kk) + 4 * kb16 + r16(cp_doubles) + r16(small_doubles) + 64 : 5 * r16(kk) + r16((size_t)k)) + 2 * r16((size_t)k);
     MOR_TRY(state.alloc(sizeof(double) * ndoubles + sizeof(long long) * (size_t)k + 64));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
-    double* W = state.as<double>();
-    double* p = W + kk;
-    double *A = nullptr, *Fm = nullptr, *C12 = nullptr, *W12 = nullptr, *Cp = nullptr, *Sinv = nullptr, *bst = nullptr,
-           *sst = nullptr, *Dsub = nullptr, *Uf = nullptr, *Lm = nullptr, *Z = nullptr, *Zt = nullptr, *c = nullptr;
+    double* p = state.as<double>();
+    auto take = [&](size_t nd) {
+        double* q = p;
+        p += r16(nd);
+        return q;
+    };
+    double *W = nullptr, *A = nullptr, *Fm = nullptr, *C12 = nullptr, *W21 = nullptr, *W12 = nullptr, *Cp = nullptr, *Sinv = nullptr,
+           *bst = nullptr, *sst = nullptr, *Dsub = nullptr, *Uf = nullptr, *Lm = nullptr, *Z = nullptr, *Zt = nullptr, *c = nullptr;
     if (blocked) {
-        A = p; p += kk;
-        Fm = p; p += (size_t)k * DEIM_BLOCK;
-        C12 = p; p += (size_t)k * DEIM_BLOCK;
-        W12 = p; p += (size_t)k * DEIM_BLOCK;
-        Cp = p; p += cp_doubles;
-        Sinv = p; p += DEIM_BLOCK * DEIM_BLOCK;
-        bst = p; p += BST_DOUBLES;
-        sst = p; p += SST_DOUBLES;
-        Dsub = p; p += DEIM_BLOCK * DEIM_SUB;
+        A = take(kk);
+        Fm = take((size_t)k * DEIM_BLOCK);
+        C12 = take((size_t)k * DEIM_BLOCK);
+        W21 = take((size_t)k * DEIM_BLOCK);      // W21 and W12 are contiguous (kb16 doubles each): one all-reduce
+        W12 = take((size_t)k * DEIM_BLOCK);
+        Cp = take(cp_doubles);
+        Sinv = take(DEIM_BLOCK * DEIM_BLOCK);
+        bst = take(BST_DOUBLES);
+        sst = take(SST_DOUBLES);
+        Dsub = take(DEIM_BLOCK * DEIM_SUB);
     } else {
-        Uf = p; p += kk;
-        Lm = p; p += kk;
-        Z = p; p += kk;
-        Zt = p; p += kk;
-        c = p; p += k;
+        W = take(kk);
+        Uf = take(kk);
+        Lm = take(kk);
+        Z = take(kk);
+        Zt = take(kk);
+        c = take((size_t)k);
     }
-    double* margins_d = p; p += k;
-    double* values_d = p; p += k;
+    double* margins_d = take((size_t)k);
+    double* values_d = take((size_t)k);
     long long* idx_d = reinterpret_cast<long long*>(p);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
     unsigned long long* tail_ns_d = reinterpret_cast<unsigned long long*>(status_d + 2);
@@ -935,6 +951,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     ta.U = B;
     ta.ldU = ld;
     ta.k = (int)k;
+    ta.krec = krec;
     ta.row_offset = row_offset;
     ta.ll = cx.box_ll;
     for (int r = 0; r < cx.nranks; ++r) ta.peer_ll[r] = fused ? cx.peer_ll[r] : cx.box_ll;
@@ -971,19 +988,10 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
         const int64_t ld2 = (blocked && s0 > 0) ? ldp : ldn;
         // pipelined host ingest: columns [i, i + group_cols) are first touched by this step (the panel of a
         // block reads columns < l0 + 16 and DEIM_BLOCK == group_cols; the streaming step i reads columns <= i)
-        if (defer && i % group_cols == 0) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[i / group_cols], 0));
+        if (defer && i == 0) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[0], 0));
         if (blocked && j == 0 && l0 > 0) {
             t_upd.start();
-            const double* wsrc = W + l0;
-            int ldw = (int)k;
-            if (defer) {
-                deim_gather_block_kernel<<<(l0 + 7) / 8, 128, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, W12);
-                count_launch();
-                if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W12, (size_t)l0 * DEIM_BLOCK));
-                wsrc = W12;
-                ldw = DEIM_BLOCK;
-            }
-            deim_coef_kernel<<<(l0 + 7) / 8, 256, 0, cx.stream>>>(A, (int)k, l0, bw, wsrc, ldw, Cp, C12);
+            deim_coef_kernel<<<(l0 + 7) / 8, 256, 0, cx.stream>>>(A, (int)k, l0, bw, W12, DEIM_BLOCK, Cp, C12);
             count_launch();
             t_upd.stop();
             t_panel.start();
@@ -991,7 +999,6 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             t_panel.stop();
         }
         ta.i = i;
-        ta.kcols = defer ? l0 + bw : (int)k;
         ta.Pn = blocked && m > 0 ? Pn : nullptr;
         ta.ldn = ldn;
         ta.bw = bw;
@@ -1027,11 +1034,24 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             deim_update_kernel<<<1, 1024, 0, cx.stream>>>(W, Uf, Lm, Z, Zt, c, i, (int)k, ta.last, status_d);
             count_launch();
         } else if (j == bw - 1 && l0 + bw < (int)k) {
-            // the panel is complete: extend A = inv(P'U) by its bw rows / columns (block-inverse formula)
+            // The panel is complete.  Fetch the two pieces of P'U that are needed now (the rows of the new points in
+            // the earlier columns, the rows of all points in the NEXT panel's columns), then extend A = inv(P'U) by
+            // the panel's bw rows / columns (block-inverse formula with the panel's own LU factors).
             t_upd.start();
+            const int l1 = l0 + bw, bwn = (int)(k - l1 < DEIM_BLOCK ? k - l1 : DEIM_BLOCK);
+            // pipelined host ingest: the next panel's columns must have landed before their rows are gathered
+            if (defer) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[l1 / group_cols], 0));
+            MOR_CUDA(cudaMemsetAsync(W21, 0, 2 * sizeof(double) * kb16, cx.stream));   // W21 | W12
+            if (l0 > 0) {
+                deim_gather_kernel<<<(bw * l0 + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, l1, 0, l0, W21, l0);
+                count_launch();
+            }
+            deim_gather_kernel<<<(l1 * bwn + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, 0, l1, l1, bwn, W12, DEIM_BLOCK);
+            count_launch();
+            if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W21, 2 * kb16));
             deim_sinv_kernel<<<1, DEIM_BLOCK * DEIM_BLOCK, 0, cx.stream>>>(bst, bw, (int)k, l0, Sinv, A);
             if (l0 > 0) {
-                deim_inv_f_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(A, W, (int)k, l0, bw, Sinv, Fm);
+                deim_inv_f_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(A, W21, (int)k, l0, bw, Sinv, Fm);
                 deim_inv_update_kernel<<<dim3((l0 + bw + 15) / 16, (l0 + 15) / 16), 256, 0, cx.stream>>>(A, (int)k, l0, bw, C12,
                                                                                                    Fm, Sinv);
                 count_launch(2);
@@ -1218,14 +1238,20 @@ int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb
     MOR_ARG(m >= 0 && k >= 1 && ldb >= (m > 0 ? m : 1), "mor_b200_deim_indices: bad dimensions");
     MOR_TRY(require_ctx());
     Ctx& cx = ctx();
-    mor_mat_t d = nullptr;
-    MOR_TRY(mor_b200_mat_alloc(m, k, &d));
+    // device copy of the basis: large ones reuse the parked ingest buffer (a cudaMalloc / cudaFree pair of tens of GB
+    // costs ~0.1 s and serialises the GPUs of a process)
+    struct Dev { double* p; int64_t m, n, ld; } dv{nullptr, m, k, std::max<int64_t>((m + 1) & ~int64_t(1), 2)};
+    DevBuf dbuf;
+    MOR_TRY(ingest_alloc(dbuf, sizeof(double) * (size_t)dv.ld * (size_t)k));
+    dv.p = dbuf.as<double>();
+    if (dv.ld != m) MOR_CUDA(cudaMemset2DAsync(dv.p + m, (size_t)dv.ld * 8, 0, 8, (size_t)k, cx.stream));   // keep the pad row finite
+    Dev* d = &dv;
     // Pipelined ingest: the basis travels in groups of 16 columns on an upload stream; the greedy loop touches
     // columns left to right (a panel needs the columns up to its own), so it starts on group 0 while the rest is
     // still on the PCIe link -- the 34 GB of a 16M x 256 basis hide all but the last panel of the computation.
     constexpr int GROUP = DEIM_BLOCK;
     const int ngroups = (int)((k + GROUP - 1) / GROUP);
-    std::vector<cudaEvent_t> ev((size_t)ngroups + 2, nullptr);   // [ngroups] = start of the upload, [ngroups+1] = pad memset done
+    std::vector<cudaEvent_t> ev((size_t)ngroups + 2, nullptr);   // [ngroups] = start of the upload, [ngroups+1] = pad row zeroed
     int32_t st = MOR_OK;
     auto cu = [&](cudaError_t e, const char* what) {
         if (st == MOR_OK && e != cudaSuccess) st = cuda_fail(e, what, __FILE__, __LINE__);
@@ -1233,7 +1259,7 @@ int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb
     if (!cx.aux_stream) cu(cudaStreamCreateWithFlags(&cx.aux_stream, cudaStreamNonBlocking), "cudaStreamCreate(aux)");
     for (auto& e : ev) cu(cudaEventCreate(&e), "cudaEventCreate");
     if (st == MOR_OK) {
-        cu(cudaEventRecord(ev[(size_t)ngroups + 1], cx.stream), "cudaEventRecord");   // mat_alloc zeroes the pad row on cx.stream
+        cu(cudaEventRecord(ev[(size_t)ngroups + 1], cx.stream), "cudaEventRecord");   // the pad row is zeroed on cx.stream
         cu(cudaStreamWaitEvent(cx.aux_stream, ev[(size_t)ngroups + 1], 0), "cudaStreamWaitEvent");
         cu(cudaEventRecord(ev[(size_t)ngroups], cx.aux_stream), "cudaEventRecord");
         for (int g = 0; g < ngroups && st == MOR_OK; ++g) {
@@ -1250,7 +1276,7 @@ int32_t mor_b200_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb
     }
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
-    mor_b200_mat_free(d);
+    cudaStreamSynchronize(cx.stream);
     return st;
 }
 

@@ -176,15 +176,16 @@ int32_t h2d_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t
     return MOR_OK;
 }
 
-// Returns after the data is in `dst` (the staged path has to copy out of the ring on the host anyway).
-int32_t d2h_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st) {
+// sync: return after the data is in `dst`.  The staged path always does (it copies out of the ring on the host); a
+// page-locked destination with sync == false only enqueues the DMA on `st`.
+int32_t d2h_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st, bool sync) {
     if (rows <= 0 || cols <= 0) return MOR_OK;
     Ctx& c = ctx();
     static const bool force_stage = getenv("MOR_B200_INGEST_FORCE_STAGING") != nullptr;
     if ((host_is_pinned(dst) && !force_stage) || (size_t)rows * cols * 8 < (size_t(1) << 20)) {
         MOR_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols,
                                    cudaMemcpyDeviceToHost, st));
-        MOR_CUDA(cudaStreamSynchronize(st));
+        if (sync) MOR_CUDA(cudaStreamSynchronize(st));
         return MOR_OK;
     }
     MOR_TRY(stage_ready(c));

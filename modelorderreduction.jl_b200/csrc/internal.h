@@ -86,7 +86,8 @@ bool host_is_pinned(const void* p);
 // staging ring.  h2d is asynchronous on `st` (the host thread is busy while it fills staging buffers); d2h returns
 // when the data is in place.
 int32_t h2d_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st);
-int32_t d2h_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st);
+int32_t d2h_2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t st,
+               bool sync = true);
 void multi_skip_env();
 const std::string& last_error_string();
 // The context of the calling thread: the process-wide one (one process per GPU), or -- inside a worker thread of the

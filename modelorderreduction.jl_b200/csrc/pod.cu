@@ -700,13 +700,47 @@ int32_t mor_b200_pod_basis(mor_pod_t h, int64_t k, double* U_out, int64_t ldu, d
     double* small_host = h->wide ? U_out : V_out;
     const int64_t small_ld = h->wide ? ldu : ldv;
     if (tall_host && h->trows > 0) {
+        // U = T * M in blocks of 16 columns through two device buffers: block c+1 is computed while block c travels
+        // to the host on the copy stream (the whole m x k result need not fit next to a 137 GB snapshot matrix, and
+        // its 8.6 GB no longer cost a cudaMalloc / cudaFree pair per call)
         const int64_t ldd = std::max<int64_t>((h->trows + 1) & ~int64_t(1), 2);
-        DevBuf dU;
-        MOR_TRY(dU.alloc(sizeof(double) * (size_t)ldd * (size_t)k));
-        MOR_TRY(tall_vectors(h, (int)k, dU.as<double>(), ldd, tm));
-        tm.d2h.start();
-        MOR_TRY(d2h_2d(tall_host, tall_ld, dU.as<double>(), ldd, h->trows, k, cx.stream));
-        tm.d2h.stop();
+        constexpr int CB = 16;
+        const int nblk = (int)((k + CB - 1) / CB);
+        DevBuf dU[2];
+        for (int b = 0; b < 2 && b < nblk; ++b) MOR_TRY(dU[b].alloc(sizeof(double) * (size_t)ldd * (size_t)std::min<int64_t>(CB, k)));
+        if (!cx.copy_stream) MOR_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
+        struct Ev {
+            cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+            ~Ev() {
+                for (int b = 0; b < 2; ++b) {
+                    if (done[b]) cudaEventDestroy(done[b]);
+                    if (copied[b]) cudaEventDestroy(copied[b]);
+                }
+            }
+        } ev;
+        for (int b = 0; b < 2; ++b) {
+            MOR_CUDA(cudaEventCreateWithFlags(&ev.done[b], cudaEventDisableTiming));
+            MOR_CUDA(cudaEventCreateWithFlags(&ev.copied[b], cudaEventDisableTiming));
+        }
+        auto compute = [&](int blk) -> int32_t {
+            const int b = blk & 1, c0 = blk * CB, nc = (int)std::min<int64_t>(CB, k - c0);
+            if (blk >= 2) MOR_CUDA(cudaStreamWaitEvent(cx.stream, ev.copied[b], 0));   // the buffer's previous block has left
+            tm.basis.start();
+            MOR_TRY(gemm_nn(h->T, h->ldt, h->tn, h->M.as<double>() + (size_t)c0 * h->tn, h->tn, nc, h->trows, dU[b].as<double>(), ldd, 0));
+            tm.basis.stop();
+            MOR_CUDA(cudaEventRecord(ev.done[b], cx.stream));
+            return MOR_OK;
+        };
+        MOR_TRY(compute(0));
+        for (int blk = 0; blk < nblk; ++blk) {
+            if (blk + 1 < nblk) MOR_TRY(compute(blk + 1));
+            const int b = blk & 1, c0 = blk * CB, nc = (int)std::min<int64_t>(CB, k - c0);
+            MOR_CUDA(cudaStreamWaitEvent(cx.copy_stream, ev.done[b], 0));
+            MOR_TRY(d2h_2d(tall_host + (size_t)c0 * tall_ld, tall_ld, dU[b].as<double>(), ldd, h->trows, nc, cx.copy_stream, /*sync=*/false));
+            MOR_CUDA(cudaEventRecord(ev.copied[b], cx.copy_stream));
+        }
+        MOR_CUDA(cudaStreamSynchronize(cx.copy_stream));
+        MOR_CUDA(cudaStreamSynchronize(cx.stream));
     }
     if (small_host) {
         tm.d2h.start();
