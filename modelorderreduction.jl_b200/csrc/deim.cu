@@ -280,6 +280,9 @@ __device__ __forceinline__ void deim_prefetch_state(const TailArgs& a, TailSmem&
 __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2, TailSmem& ts) {
     const int tid = threadIdx.x, k = a.krec, rec = a.rec;
     unsigned long long t0 = 0;
+    // every other CTA of this grid has exited: the next step's grid may take the idle SMs now (it waits for this
+    // grid's completion before it reads anything)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
         ts.fail = 0;
@@ -415,6 +418,9 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l, con
     __shared__ double sv[DEIM_WARPS], ss2[DEIM_WARPS];
     __shared__ long long si[DEIM_WARPS];
     const int tid = threadIdx.x;
+    // Programmatic dependent launch: this grid may have been scheduled while the previous step's tail was still
+    // running in its last CTA; nothing of that step (coefficients, ticket) is touched before it has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int j = tid; j < l; j += DEIM_THREADS) sc[j] = cg[j];
     __syncthreads();
 
@@ -522,6 +528,7 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
     __shared__ long long si[DEIM_WARPS];
     double* sd = sbuf;
     const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // see deim_step_kernel
     if (tid < DEIM_BLOCK * DEIM_SUB) sd[tid] = Dg[tid];
     __syncthreads();
 
@@ -701,15 +708,24 @@ deim_update_kernel(const double* __restrict__ Wm, double* __restrict__ Uf, doubl
 // basis (each rank contributes the rows it owns, zeros elsewhere; the host all-reduces them when there are several):
 //   W21[c][t] = U[idx[l0 + c], t],       t < l0              (rows of the panel's new points, earlier columns)
 //   W12[t][q] = U[idx[t], l1 + q],       t < l1 = l0 + bw    (rows of all points so far, the next panel's columns)
-// out[(t - t0) * ldo + (c - c0)] = U[idx[t], c] for t in [t0, t1), c in [c0, c0 + nc)
+// One launch writes both (zeros for rows owned by other ranks and for the padding columns of W12):
+//   W21 (bw x l0, row-major, stride l0) then W12 (l1 x 16, row-major)
 __global__ void __launch_bounds__(256)
 deim_gather_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset, const long long* __restrict__ idx,
-                   int t0, int t1, int c0, int nc, double* __restrict__ out, int ldo) {
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    const int t = t0 + e / nc, c = e % nc;
-    if (t >= t1) return;
+                   int l0, int bw, int bwn, double* __restrict__ W21, double* __restrict__ W12) {
+    const int l1 = l0 + bw, n21 = bw * l0;
+    int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < n21) {
+        const int c = e / l0, t = e % l0;
+        const long long loc = idx[l0 + c] - 1 - row_offset;
+        W21[e] = (loc >= 0 && loc < m) ? U[loc + (int64_t)t * ld] : 0.0;
+        return;
+    }
+    e -= n21;
+    if (e >= l1 * DEIM_BLOCK) return;
+    const int t = e / DEIM_BLOCK, q = e % DEIM_BLOCK;
     const long long loc = idx[t] - 1 - row_offset;
-    out[(size_t)(t - t0) * ldo + c] = (loc >= 0 && loc < m) ? U[loc + (int64_t)(c0 + c) * ld] : 0.0;
+    W12[e] = (q < bwn && loc >= 0 && loc < m) ? U[loc + (int64_t)(l1 + q) * ld] : 0.0;
 }
 
 // Coefficients of the panel that starts at column l0:  C = A[0:l0, 0:l0] * W12  (column q of C solves
@@ -744,47 +760,26 @@ deim_coef_kernel(const double* __restrict__ A, int k, int l0, int bw, const doub
     }
 }
 
-// Panel end, step 1: Sinv = inv(S) = Z * inv(L) of the panel's pivot block S = P'R = L * Uf (16 x 16, unit lower L),
-// and the new diagonal block A[l0:l0+bw, l0:l0+bw] = Sinv.
-__global__ void __launch_bounds__(DEIM_BLOCK * DEIM_BLOCK)
-deim_sinv_kernel(const double* __restrict__ bst, int bw, int k, int l0, double* __restrict__ Sinv, double* __restrict__ A) {
-    __shared__ double L[DEIM_BLOCK * DEIM_BLOCK], Z[DEIM_BLOCK * DEIM_BLOCK], Li[DEIM_BLOCK * DEIM_BLOCK];
-    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK;
-    const int tid = threadIdx.x, a = tid / DEIM_BLOCK, b = tid % DEIM_BLOCK;
-    L[tid] = bst[BB + tid];
-    Z[tid] = bst[2 * BB + tid];
-    Li[tid] = a == b ? 1.0 : 0.0;
-    __syncthreads();
-    if (tid < bw) {   // column tid of inv(L) by forward substitution (L unit lower; strictly lower part stored)
-        const int cc = tid;
-        for (int r = cc + 1; r < bw; ++r) {
-            double s = 0.0;
-            for (int t = cc; t < r; ++t) s = fma(L[r * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + cc], s);
-            Li[r * DEIM_BLOCK + cc] = -s;
-        }
-    }
-    __syncthreads();
-    double s = 0.0;
-    if (a < bw && b < bw)
-        for (int t = (a > b ? a : b); t < bw; ++t) s = fma(Z[a * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + b], s);
-    Sinv[tid] = s;
-    if (a < bw && b < bw) A[(size_t)(l0 + a) * k + l0 + b] = s;
-}
-
-// Panel end, step 2: F = Sinv * (W21 * A11)  (bw x l0), W21 (bw x l0, row-major, stride l0) gathered from the basis; also A21 = -F.
+// Panel end, steps 1 + 2.  Every CTA first forms Sinv = inv(S) = Z * inv(L) of the panel's pivot block S = P'R = L * Uf
+// (16 x 16, unit lower L) in shared memory (CTA 0 also stores it and the new diagonal block A[l0:l1, l0:l1] = Sinv),
+// then F = Sinv * (W21 * A11)  (bw x l0), W21 (bw x l0, row-major, stride l0) gathered from the basis; also A21 = -F.
 // One CTA per 16 columns j of A11: thread (ts, jj) accumulates rows t = ts (mod 16) of all 16 dot products of its
 // column (A[t][j] is read once, coalesced over jj), the 16 slices are summed through shared memory.
 __global__ void __launch_bounds__(256)
 deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W21, int k, int l0, int bw,
-                  const double* __restrict__ Sinv, double* __restrict__ F) {
+                  const double* __restrict__ bst, double* __restrict__ Sinv, double* __restrict__ F) {
     __shared__ double part[DEIM_BLOCK][DEIM_BLOCK][DEIM_BLOCK + 1];   // [slice][c][jj]
     __shared__ double e[DEIM_BLOCK][DEIM_BLOCK + 1], sinv[DEIM_BLOCK * DEIM_BLOCK];
+    __shared__ double Ls[DEIM_BLOCK * DEIM_BLOCK], Zs[DEIM_BLOCK * DEIM_BLOCK], Li[DEIM_BLOCK * DEIM_BLOCK];
+    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK;
     const int tid = threadIdx.x, jj = tid % DEIM_BLOCK, ts = tid / DEIM_BLOCK, j = blockIdx.x * DEIM_BLOCK + jj;
-    sinv[tid] = Sinv[tid];
+    Ls[tid] = bst[BB + tid];
+    Zs[tid] = bst[2 * BB + tid];
+    Li[tid] = ts == jj ? 1.0 : 0.0;
     double acc[DEIM_BLOCK];
 #pragma unroll
     for (int c = 0; c < DEIM_BLOCK; ++c) acc[c] = 0.0;
-    if (j < l0)
+    if (j < l0)   // the long loads first: they overlap the small triangular work below
         for (int t = ts; t < l0; t += DEIM_BLOCK) {
             const double av = __ldcg(&A[(size_t)t * k + j]);
 #pragma unroll
@@ -793,12 +788,32 @@ deim_inv_f_kernel(double* __restrict__ A, const double* __restrict__ W21, int k,
 #pragma unroll
     for (int c = 0; c < DEIM_BLOCK; ++c) part[ts][c][jj] = acc[c];
     __syncthreads();
+    if (tid < bw) {   // column tid of inv(L) by forward substitution (L unit lower; strictly lower part stored)
+        const int cc = tid;
+        for (int r = cc + 1; r < bw; ++r) {
+            double s = 0.0;
+            for (int t = cc; t < r; ++t) s = fma(Ls[r * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + cc], s);
+            Li[r * DEIM_BLOCK + cc] = -s;
+        }
+    }
     {
         const int c = ts;   // thread (c, jj) sums the slices of E[c][j]
         double s = 0.0;
 #pragma unroll
         for (int sl = 0; sl < DEIM_BLOCK; ++sl) s += part[sl][c][jj];
         e[c][jj] = s;
+    }
+    __syncthreads();
+    {
+        const int a = ts, b = jj;
+        double s = 0.0;
+        if (a < bw && b < bw)
+            for (int t = (a > b ? a : b); t < bw; ++t) s = fma(Zs[a * DEIM_BLOCK + t], Li[t * DEIM_BLOCK + b], s);
+        sinv[tid] = s;
+        if (blockIdx.x == 0) {
+            Sinv[tid] = s;
+            if (a < bw && b < bw) A[(size_t)(l0 + a) * k + l0 + b] = s;
+        }
     }
     __syncthreads();
     const int c = ts;
@@ -844,6 +859,23 @@ static double deim_tie_tol(int64_t k) {
     if (off && off[0] == '0') return -1.0;
     const char* e = getenv("MOR_B200_DEIM_TIE_TOL");
     return e ? atof(e) : 32.0 * (double)k * 2.220446049250313e-16;
+}
+
+// Launch a step kernel; `pdl`: the previous operation on the stream was a step kernel too, so this grid may be
+// scheduled as soon as that one's CTAs have exited or reached their tail (programmatic stream serialization).
+template <class... KArgs, class... Args>
+static cudaError_t launch_step(void (*kern)(KArgs...), int grid, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(DEIM_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64_t* idx_host, const cudaEvent_t* col_ready,
@@ -971,6 +1003,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     ta.status = status_d;
     ta.tail_ns = tail_ns_d;
 
+    static const bool use_pdl = !(getenv("MOR_B200_DEIM_PDL") && getenv("MOR_B200_DEIM_PDL")[0] == '0');
     Timer t_total(MOR_T_TOTAL), t_panel(MOR_T_DEIM_PANEL), t_upd(MOR_T_DEIM_UPDATE);
     t_total.start();
     for (int i = 0; i < (int)k; ++i) {
@@ -1012,12 +1045,14 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
         const unsigned long long seq = cx.deim_seq + (unsigned long long)i;
         ta.slot = (int)(seq % DEIM_SLOTS);
         ta.tag = (unsigned)(seq % 0xfffffff0ull) + 1u;   // never 0 (a zeroed mailbox matches no step)
+        const bool pdl = use_pdl && blocked && fused && j > 0;   // the stream's previous operation was a step kernel
         if (blocked && s0 > 0 && jj == 0) {
             // residuals of the next 4 panel columns in one pass over the s0 earlier ones, fused with this step's argmax
-            deim_step4_kernel<R><<<grid, DEIM_THREADS, 0, cx.stream>>>(Pn, m, ldn, s0, sw, Dsub, R2, ldp, row_offset, ta);
+            MOR_CUDA(launch_step(deim_step4_kernel<R>, grid, cx.stream, pdl, Pn, m, ldn, s0, sw, (const double*)Dsub, R2, ldp,
+                                 row_offset, ta));
         } else if (blocked) {
-            deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(P2, m, ld2, jj, sst + 3 * DEIM_SUB * DEIM_SUB,
-                                                                            row_offset, ta);
+            MOR_CUDA(launch_step(deim_step_kernel<R, true>, grid, cx.stream, pdl, P2, m, ld2, jj,
+                                 (const double*)(sst + 3 * DEIM_SUB * DEIM_SUB), row_offset, ta));
         } else if (vec) {
             deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, ta);
         } else {
@@ -1041,21 +1076,18 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             const int l1 = l0 + bw, bwn = (int)(k - l1 < DEIM_BLOCK ? k - l1 : DEIM_BLOCK);
             // pipelined host ingest: the next panel's columns must have landed before their rows are gathered
             if (defer) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[l1 / group_cols], 0));
-            MOR_CUDA(cudaMemsetAsync(W21, 0, 2 * sizeof(double) * kb16, cx.stream));   // W21 | W12
+            // W21 (bw x l0) and W12 (l1 x 16) sit back to back in one buffer: one launch, one all-reduce
+            W12 = W21 + r16((size_t)bw * l0);
+            deim_gather_kernel<<<(bw * l0 + l1 * DEIM_BLOCK + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, bwn,
+                                                                                           W21, W12);
+            if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W21, r16((size_t)bw * l0) + (size_t)l1 * DEIM_BLOCK));
+            deim_inv_f_kernel<<<l0 > 0 ? (l0 + DEIM_BLOCK - 1) / DEIM_BLOCK : 1, 256, 0, cx.stream>>>(A, W21, (int)k, l0, bw, bst, Sinv, Fm);
             if (l0 > 0) {
-                deim_gather_kernel<<<(bw * l0 + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, l1, 0, l0, W21, l0);
-                count_launch();
-            }
-            deim_gather_kernel<<<(l1 * bwn + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, 0, l1, l1, bwn, W12, DEIM_BLOCK);
-            count_launch();
-            if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W21, 2 * kb16));
-            deim_sinv_kernel<<<1, DEIM_BLOCK * DEIM_BLOCK, 0, cx.stream>>>(bst, bw, (int)k, l0, Sinv, A);
-            if (l0 > 0) {
-                deim_inv_f_kernel<<<(l0 + DEIM_BLOCK - 1) / DEIM_BLOCK, 256, 0, cx.stream>>>(A, W21, (int)k, l0, bw, Sinv, Fm);
                 deim_inv_update_kernel<<<dim3((l0 + bw + 15) / 16, (l0 + 15) / 16), 256, 0, cx.stream>>>(A, (int)k, l0, bw, C12,
                                                                                                    Fm, Sinv);
-                count_launch(2);
+                count_launch();
             }
+            count_launch();
             count_launch();
             t_upd.stop();
         }
