@@ -255,8 +255,6 @@ void teardown_device(Ctx& c) {
     c.copy_stream = nullptr;
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
     c.aux_stream = nullptr;
-    if (c.server_stream) cudaStreamDestroy(c.server_stream);
-    c.server_stream = nullptr;
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     c.own_stream = nullptr;
     c.stream = nullptr;

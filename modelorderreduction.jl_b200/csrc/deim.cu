@@ -142,37 +142,6 @@ __device__ __forceinline__ bool ll_load(const uint4* p, unsigned tag, double& v,
     return true;
 }
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-constexpr long long SPIN_DEADLINE = 1LL << 36;   // ~35 s of SM clocks: a peer / the server died; fail instead of hanging
-
-// block until the server has finished the tail of greedy step `need` (1-based count); all threads of the CTA call it
-__device__ __forceinline__ void wait_steps(const unsigned* step_flag, unsigned need, int* status) {
-    if (need == 0) return;
-    if (threadIdx.x == 0) {
-        const long long c0 = clock64();
-        while (ld_acquire_gpu_u32(step_flag) < need) {
-            if (clock64() - c0 > SPIN_DEADLINE) {
-                atomicExch(status, -2);
-                break;
-            }
-            __nanosleep(100);
-        }
-    }
-    __syncthreads();
-}
-
 // Everything the fused tail needs (passed by value to the step kernels).
 struct TailArgs {
     unsigned* ticket;                 // last-CTA election
@@ -195,11 +164,7 @@ struct TailArgs {
     double* send;                     // NCCL fallback: the local record goes here instead
     int rank, nranks, rec, slot;
     unsigned tag;                     // this step's number (never 0)
-    int mode;                         // 0: fused (local + peer exchange + global), 1: local part only (NCCL follows),
-                                      // 2: the tail runs in the resident server CTA (deim_server_kernel)
-    unsigned long long* done_ctas;    // mode 2: every CTA of a step kernel counts itself here when its candidates are out
-    const unsigned* step_flag;        // mode 2: number of greedy steps whose tail is complete
-    unsigned need;                    // mode 2: this launch may read coefficients once *step_flag >= need
+    int mode;                         // 0: fused (local + peer exchange + global), 1: local part only (NCCL follows)
     // global part
     double* W;                        // streaming path: k x k rows of the basis at the chosen points (row-major)
     long long* idx_out;
@@ -217,36 +182,33 @@ struct TailArgs {
 // One bordered (Doolittle) update of a small LU state by ONE warp: append row i (values w[0..dim)), then solve for
 // the coefficients of column i + 1.  The greedy choice is partial pivoting, so no row exchanges are needed and the
 // factorisation equals dgetrf's.  Z = inv(Uf) is kept explicitly: every phase is a set of independent dot products.
-// S = row stride of the state.  Deliberately NOT inlined / unrolled: the tail runs once per launch in one CTA with a
-// cold instruction cache, so its cost is the number of instruction bytes fetched, not the number executed.
-__device__ __noinline__ void bordered_update_warp(double* Uf, double* L, double* Z, double* c, int S, int i, int dim,
-                                                  const double* w) {
+template <int S>
+__device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, double* Z, double* c, int i, int dim,
+                                                     const double* w) {
     const int x = threadIdx.x & 31;
     if (x < i) {   // L row i:  ell[x] = sum_{t <= x} w[t] Z[t][x]
         double s = 0.0;
-#pragma unroll 1
         for (int t = 0; t <= x; ++t) s = fma(w[t], Z[t * S + x], s);
         L[i * S + x] = s;
     }
     __syncwarp();
     if (x >= i && x < dim) {   // U-factor row i:  Uf[i][x] = w[x] - sum_{t < i} ell[t] Uf[t][x]
         double s = 0.0;
-#pragma unroll 1
         for (int t = 0; t < i; ++t) s = fma(L[i * S + t], Uf[t * S + x], s);
         Uf[i * S + x] = w[x] - s;
     }
     __syncwarp();
     const double pivot = Uf[i * S + i];
-    if (x <= i) {   // Z column i:  Z[x][i] = -(sum_{t = x}^{i-1} Z[x][t] Uf[t][i]) / pivot,  Z[i][i] = 1 / pivot
-        double s = x == i ? -1.0 : 0.0;
-#pragma unroll 1
+    if (x < i) {   // Z column i:  Z[x][i] = -(sum_{t = x}^{i-1} Z[x][t] Uf[t][i]) / pivot
+        double s = 0.0;
         for (int t = x; t < i; ++t) s = fma(Z[x * S + t], Uf[t * S + i], s);
         Z[x * S + i] = -s / pivot;
+    } else if (x == i) {
+        Z[i * S + i] = 1.0 / pivot;
     }
     __syncwarp();
     if (i + 1 < dim && x <= i) {   // c = Z[0:i+1, 0:i+1] * Uf[0:i+1, i+1]
         double s = 0.0;
-#pragma unroll 1
         for (int t = x; t <= i; ++t) s = fma(Z[x * S + t], Uf[t * S + i + 1], s);
         c[x] = s;
     }
@@ -280,21 +242,16 @@ __device__ __forceinline__ void deim_pick_winner(const TailArgs& a, TailSmem& ts
 }
 
 // Last part of the tail: `wrec` (shared memory) is the winner's record, ts.st the small LU states.
-__device__ __noinline__ void deim_tail_finish(const TailArgs& a, const double* wrec, TailSmem& ts) {
+__device__ void deim_tail_finish(const TailArgs& a, const double* wrec, TailSmem& ts) {
     const int tid = threadIdx.x, k = a.krec;
     for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = wrec[2 + jx];
     if (!a.blocked) return;
-    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK;
+    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK, SS = DEIM_SUB * DEIM_SUB;
     double* bs = ts.st;
     double* ss = ts.st + BST_DOUBLES;
     const int warp = tid >> 5;
-    if (warp < 2) {   // warp 0: the panel's 16 x 16 state, warp 1: the sub-panel's 4 x 4 state -- one copy of the code
-        const bool big = warp == 0;
-        double* st = big ? bs : ss;
-        const int S = big ? DEIM_BLOCK : DEIM_SUB, SQ = S * S;
-        bordered_update_warp(st, st + SQ, st + 2 * SQ, st + 3 * SQ, S, big ? a.j : a.jj, big ? a.bw : a.sw,
-                             wrec + 2 + k + (big ? 0 : DEIM_BLOCK));
-    }
+    if (warp == 0) bordered_update_warp<DEIM_BLOCK>(bs, bs + BB, bs + 2 * BB, bs + 3 * BB, a.j, a.bw, wrec + 2 + k);
+    if (warp == 1) bordered_update_warp<DEIM_SUB>(ss, ss + SS, ss + 2 * SS, ss + 3 * SS, a.jj, a.sw, wrec + 2 + k + DEIM_BLOCK);
     __syncthreads();
     // the pivot is the residual at the chosen row: exactly zero <=> P'U singular (SingularException in the reference)
     if (tid == 0 && bs[a.j * DEIM_BLOCK + a.j] == 0.0 && !a.last && *a.status == 0) *a.status = a.i + 1;
@@ -320,7 +277,7 @@ __device__ __forceinline__ void deim_prefetch_state(const TailArgs& a, TailSmem&
 }
 
 // The tail, entered by every thread of the LAST CTA of a step kernel.  sbuf: >= rec doubles of shared memory.
-__device__ __noinline__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2, TailSmem& ts) {
+__device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long* si, double* ss2, TailSmem& ts) {
     const int tid = threadIdx.x, k = a.krec, rec = a.rec;
     unsigned long long t0 = 0;
     // every other CTA of this grid has exited: the next step's grid may take the idle SMs now (it waits for this
@@ -450,193 +407,6 @@ __global__ void __launch_bounds__(DEIM_THREADS) deim_tail_global_kernel(TailArgs
     deim_tail_finish(a, sbuf, ts);
 }
 
-// ---- the tail as a resident server -------------------------------------------------------------------------------
-// One CTA, launched once per DEIM call on a side stream, stays resident for all k greedy steps of the blocked path: it
-// waits until every CTA of step kernel i has reported its candidate, then does what deim_tail does -- reduce, gather
-// the winner's rows, exchange with the peers, pick the global winner, extend the small LU factors, publish the next
-// coefficients -- and releases step i + 1.  Why a server: executed once per launch by whichever CTA finishes last, the
-// tail ran with a cold instruction cache (~45 KB of code) and re-read its state from L2 every step: 11 us per step
-// measured at one GPU against ~4 us of dependent memory latency.  Here the loop stays hot, the LU factors never leave
-// shared memory, and the next step kernel's launch latency overlaps the tail instead of following it.
-struct ServerArgs {
-    int k, grid;
-    int64_t m, row_offset, ld, ldp;
-    const double* B;                  // basis shard
-    const double* panel;              // residual panel (ldp x 16), sub-panel right behind it
-    const double* R2;
-    const Cand* cands;
-    const unsigned long long* done_ctas;
-    unsigned* step_flag;
-    uint4* ll;
-    uint4* peer_ll[DEIM_MAXRANKS];
-    int rank, nranks;
-    unsigned long long seq0;
-    long long* idx_out;
-    double *margins, *values;
-    double *csub, *Dsub, *bst;        // published: in-sub-panel coefficients (4), next sub-panel's (16 x 4), panel factors
-    int* status;
-    unsigned long long* tail_ns;
-};
-
-__global__ void __launch_bounds__(DEIM_THREADS) deim_server_kernel(ServerArgs a) {
-    __shared__ double rec[DEIM_BLOCK + DEIM_SUB + 3];
-    __shared__ double sv[DEIM_WARPS], ss2[DEIM_WARPS];
-    __shared__ long long si[DEIM_WARPS];
-    __shared__ TailSmem ts;
-    constexpr int REC = DEIM_BLOCK + DEIM_SUB + 3, BB = DEIM_BLOCK * DEIM_BLOCK, SQ = DEIM_SUB * DEIM_SUB;
-    const int tid = threadIdx.x, warp = tid >> 5, k = a.k;
-    for (int e = tid; e < BST_DOUBLES + SST_DOUBLES; e += DEIM_THREADS) ts.st[e] = 0.0;
-    if (tid == 0) ts.fail = 0;
-    __syncthreads();
-    double* bs = ts.st;
-    double* ss = ts.st + BST_DOUBLES;
-#pragma unroll 1
-    for (int i = 0; i < k; ++i) {
-        const int l0 = (i / DEIM_BLOCK) * DEIM_BLOCK, j = i - l0, bw = k - l0 < DEIM_BLOCK ? k - l0 : DEIM_BLOCK;
-        const int s0 = (j / DEIM_SUB) * DEIM_SUB, jj = j - s0, sw = bw - s0 < DEIM_SUB ? bw - s0 : DEIM_SUB;
-        const double* Pn = l0 > 0 ? a.panel : a.B;
-        const int64_t ldn = l0 > 0 ? a.ldp : a.ld;
-        const double* P2 = s0 > 0 ? a.R2 : Pn + (int64_t)s0 * ldn;
-        const int64_t ld2 = s0 > 0 ? a.ldp : ldn;
-        unsigned long long t0 = 0;
-        if (tid == 0) {   // every CTA of step kernel i has written its candidate
-            const unsigned long long target = (unsigned long long)(i + 1) * (unsigned long long)a.grid;
-            const long long c0 = clock64();
-            while (ld_acquire_gpu_u64(a.done_ctas) < target) {
-                if (clock64() - c0 > SPIN_DEADLINE) {
-                    ts.fail = 2;
-                    break;
-                }
-            }
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-        }
-        __syncthreads();
-        // (a) this rank's winner: all loads first (independent L2 round trips), then the merges
-        constexpr int PER = 6;   // grid <= 8 * 148 + slack
-        double cv[PER], c2[PER];
-        long long ci[PER];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int t = tid + u * DEIM_THREADS;
-            const bool in = t < a.grid;
-            cv[u] = in ? __ldcg(&a.cands[t].val) : -1.0;
-            ci[u] = in ? __ldcg(&a.cands[t].idx) : MOR_IDX_NONE;
-            c2[u] = in ? __ldcg(&a.cands[t].val2) : -1.0;
-        }
-        double bv = -1.0, b2 = -1.0;
-        long long bi = MOR_IDX_NONE;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) cand_merge(bv, bi, b2, cv[u], ci[u], c2[u]);
-        for (int t = tid + PER * DEIM_THREADS; t < a.grid; t += DEIM_THREADS)
-            cand_merge(bv, bi, b2, __ldcg(&a.cands[t].val), __ldcg(&a.cands[t].idx), __ldcg(&a.cands[t].val2));
-        cand_block_reduce(bv, bi, b2, sv, si, ss2);
-        if (tid == 0) {
-            ts.widx = bi;
-            rec[0] = bv;
-            rec[1] = __longlong_as_double(bi);
-            rec[REC - 1] = b2;
-            ts.hv[a.rank] = bv;
-            ts.hi[a.rank] = bi;
-            ts.h2[a.rank] = b2;
-        }
-        __syncthreads();
-        // (b) the winner's rows of the panel and of the sub-panel
-        const long long g = ts.widx;
-        if (tid < DEIM_BLOCK)
-            rec[2 + tid] = (g == MOR_IDX_NONE || tid >= bw) ? 0.0 : __ldcg(&Pn[(g - a.row_offset) + (int64_t)tid * ldn]);
-        if (tid >= 32 && tid < 32 + DEIM_SUB) {
-            const int q = tid - 32;
-            rec[2 + DEIM_BLOCK + q] = (g == MOR_IDX_NONE || q >= sw) ? 0.0 : __ldcg(&P2[(g - a.row_offset) + (int64_t)q * ld2]);
-        }
-        __syncthreads();
-        // (c) exchange
-        if (a.nranks > 1) {
-            const unsigned long long seq = a.seq0 + (unsigned long long)i;
-            const int slot = (int)(seq % DEIM_SLOTS);
-            const unsigned tag = (unsigned)(seq % 0xfffffff0ull) + 1u;
-            const size_t my_off = ((size_t)slot * DEIM_MAXRANKS + a.rank) * DEIM_REC_MAX;
-            if (tid < REC) {
-                const double v = rec[tid];
-                for (int p = 0; p < a.nranks; ++p)
-                    if (p != a.rank) ll_store(a.peer_ll[p] + my_off + tid, v, tag);
-            }
-            const long long deadline = clock64() + SPIN_DEADLINE;
-            if (tid < a.nranks && tid != a.rank) {
-                const uint4* src = a.ll + ((size_t)slot * DEIM_MAXRANKS + tid) * DEIM_REC_MAX;
-                double v = -1.0, ib = 0.0, s2 = -1.0;
-                const bool ok = ll_load(src, tag, v, deadline) && ll_load(src + 1, tag, ib, deadline) &&
-                                ll_load(src + REC - 1, tag, s2, deadline);
-                ts.hv[tid] = v;
-                ts.hi[tid] = ok ? __double_as_longlong(ib) : MOR_IDX_NONE;
-                ts.h2[tid] = s2;
-                if (!ok) ts.fail = 1;
-            }
-            __syncthreads();
-            // (d) global winner; its rows
-            if (tid == 0) {
-                int win = 0;
-                double wv = -1.0, w2 = -1.0;
-                long long wi = MOR_IDX_NONE;
-                for (int r = 0; r < a.nranks; ++r) {
-                    const long long before = wi;
-                    cand_merge(wv, wi, w2, ts.hv[r], ts.hi[r], ts.h2[r]);
-                    if (wi != before) win = r;
-                }
-                ts.win = win;
-                rec[0] = wv;
-                rec[1] = __longlong_as_double(wi);
-                rec[REC - 1] = w2;
-            }
-            __syncthreads();
-            if (ts.win != a.rank && tid >= 2 && tid < REC - 1) {
-                const uint4* src = a.ll + ((size_t)slot * DEIM_MAXRANKS + ts.win) * DEIM_REC_MAX;
-                double v = 0.0;
-                if (!ll_load(src + tid, tag, v, deadline)) ts.fail = 1;
-                rec[tid] = v;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) {
-            const double wv = rec[0], w2 = rec[REC - 1];
-            a.idx_out[i] = __double_as_longlong(rec[1]) + 1;   // 1-based, like Julia
-            a.values[i] = wv;
-            a.margins[i] = (wv == wv && wv > 0.0 && w2 >= 0.0) ? (wv - w2) / wv : (wv > 0.0 && w2 < 0.0 ? 1.0 : 0.0);
-        }
-        // (e) extend the LU factors of the panel (warp 0) and of the sub-panel (warp 1) by the winner's rows
-        if (warp < 2) {
-            const bool big = warp == 0;
-            double* st = big ? bs : ss;
-            const int S = big ? DEIM_BLOCK : DEIM_SUB, Q = S * S;
-            bordered_update_warp(st, st + Q, st + 2 * Q, st + 3 * Q, S, big ? j : jj, big ? bw : sw, rec + 2 + (big ? 0 : DEIM_BLOCK));
-        }
-        __syncthreads();
-        // the pivot is the residual at the chosen row: exactly zero <=> P'U singular (SingularException in the reference)
-        if (tid == 0 && bs[j * DEIM_BLOCK + j] == 0.0 && i != k - 1 && *a.status == 0) *a.status = i + 1;
-        // (f) publish what the next launches read
-        if (tid < DEIM_SUB) a.csub[tid] = ss[3 * SQ + tid];
-        const int s0n = s0 + sw;
-        if (jj + 1 == sw && s0n < bw && tid < DEIM_BLOCK * DEIM_SUB) {   // next step opens a new sub-panel
-            const int t = tid % DEIM_BLOCK, q = tid / DEIM_BLOCK;
-            const int swn = bw - s0n < DEIM_SUB ? bw - s0n : DEIM_SUB;
-            double s = 0.0;
-            if (t < s0n && q < swn)
-                for (int r = t; r < s0n; ++r) s = fma(bs[2 * BB + t * DEIM_BLOCK + r], bs[r * DEIM_BLOCK + s0n + q], s);
-            a.Dsub[q * DEIM_BLOCK + t] = s;
-        }
-        if (j == bw - 1)   // the panel is complete: its factors go to deim_inv_f_kernel
-            for (int e = tid; e < BST_DOUBLES; e += DEIM_THREADS) a.bst[e] = bs[e];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            if (ts.fail) atomicExch(a.status, -ts.fail);
-            st_release_gpu_u32(a.step_flag, (unsigned)(i + 1));
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-            *a.tail_ns += t1 - t0;
-        }
-    }
-}
-
 // Fused residual + abs-argmax over this rank's rows, then the tail.  l = number of previous columns.
 // VEC: 16-byte loads (needs 16B-aligned base and even ld).  Each CTA walks chunks of
 // 2*R*256 consecutive rows; for every column the CTA reads one contiguous 4*R KB run.
@@ -651,7 +421,6 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l, con
     // Programmatic dependent launch: this grid may have been scheduled while the previous step's tail was still
     // running in its last CTA; nothing of that step (coefficients, ticket) is touched before it has completed.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (ta.mode == 2) wait_steps(ta.step_flag, ta.need, ta.status);
     for (int j = tid; j < l; j += DEIM_THREADS) sc[j] = cg[j];
     __syncthreads();
 
@@ -740,14 +509,6 @@ deim_step_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int l, con
         ta.cands[blockIdx.x].idx = bi;
         ta.cands[blockIdx.x].val2 = b2;
     }
-    if (ta.mode == 2) {   // the resident server CTA does the tail: just report in
-        __syncthreads();   // (this CTA's stores, incl. thread 0's candidate, precede the fence below in program order)
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(ta.done_ctas, 1ull);
-        }
-        return;
-    }
     if (!deim_last_cta(ta.ticket)) return;
     __shared__ TailSmem ts;
     deim_tail(ta, sc, sv, si, ss2, ts);
@@ -768,7 +529,6 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
     double* sd = sbuf;
     const int tid = threadIdx.x;
     asm volatile("griddepcontrol.wait;" ::: "memory");   // see deim_step_kernel
-    if (ta.mode == 2) wait_steps(ta.step_flag, ta.need, ta.status);
     if (tid < DEIM_BLOCK * DEIM_SUB) sd[tid] = Dg[tid];
     __syncthreads();
 
@@ -843,15 +603,6 @@ deim_step4_kernel(const double* __restrict__ P1, int64_t m, int64_t ld1, int s0,
         ta.cands[blockIdx.x].val = bv;
         ta.cands[blockIdx.x].idx = bi;
         ta.cands[blockIdx.x].val2 = b2;
-    }
-    if (ta.mode == 2) {
-        __threadfence();   // every thread's R2 stores
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(ta.done_ctas, 1ull);
-        }
-        return;
     }
     if (!deim_last_cta(ta.ticket)) return;   // includes the fence that publishes this CTA's R2 stores
     __shared__ TailSmem ts;
@@ -961,10 +712,8 @@ deim_update_kernel(const double* __restrict__ Wm, double* __restrict__ Uf, doubl
 //   W21 (bw x l0, row-major, stride l0) then W12 (l1 x 16, row-major)
 __global__ void __launch_bounds__(256)
 deim_gather_kernel(const double* __restrict__ U, int64_t m, int64_t ld, int64_t row_offset, const long long* __restrict__ idx,
-                   int l0, int bw, int bwn, double* __restrict__ W21, double* __restrict__ W12, const unsigned* step_flag,
-                   int* status) {
+                   int l0, int bw, int bwn, double* __restrict__ W21, double* __restrict__ W12) {
     const int l1 = l0 + bw, n21 = bw * l0;
-    if (step_flag) wait_steps(step_flag, (unsigned)l1, status);   // server mode: the panel's points are final
     int e = blockIdx.x * 256 + threadIdx.x;
     if (e < n21) {
         const int c = e / l0, t = e % l0;
@@ -1186,7 +935,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     auto r16 = [](size_t nd) { return (nd + 15) & ~size_t(15); };
     const size_t kb16 = r16((size_t)k * DEIM_BLOCK);
     const size_t ndoubles = (blocked ? r16(kk) + 4 * kb16 + r16(cp_doubles) + r16(small_doubles) + 64 : 5 * r16(kk) + r16((size_t)k)) + 2 * r16((size_t)k);
-    MOR_TRY(state.alloc(sizeof(double) * (ndoubles + 16) + sizeof(long long) * (size_t)k + 128));
+    MOR_TRY(state.alloc(sizeof(double) * ndoubles + sizeof(long long) * (size_t)k + 64));
     MOR_TRY(cands.alloc(sizeof(Cand) * (size_t)grid));
     MOR_CUDA(cudaMemsetAsync(state.p, 0, state.bytes, cx.stream));
     double* p = state.as<double>();
@@ -1218,16 +967,9 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     }
     double* margins_d = take((size_t)k);
     double* values_d = take((size_t)k);
-    double* csub = take(16);              // server mode: coefficients of the next in-sub-panel step
     long long* idx_d = reinterpret_cast<long long*>(p);
     int* status_d = reinterpret_cast<int*>(idx_d + k);
     unsigned long long* tail_ns_d = reinterpret_cast<unsigned long long*>(status_d + 2);
-    unsigned long long* done_ctas_d = tail_ns_d + 1;
-    unsigned* step_flag_d = reinterpret_cast<unsigned*>(done_ctas_d + 1);
-    // Blocked path with a fused exchange: the per-step tail runs in a resident server CTA on a side stream
-    // (deim_server_kernel) instead of in the last CTA of every step kernel.  MOR_B200_DEIM_SERVER=0: in-kernel tails.
-    static const bool server_env = !(getenv("MOR_B200_DEIM_SERVER") && getenv("MOR_B200_DEIM_SERVER")[0] == '0');
-    const bool server = blocked && fused && server_env;
     double* R2 = blocked && m > 0 ? panel.as<double>() + (size_t)ldp * DEIM_BLOCK : nullptr;
     // pipelined ingest: later columns of the basis are not there yet, so a record carries the winner's row only up
     // to the current panel and the rest is gathered at each panel boundary
@@ -1249,9 +991,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     ta.rank = cx.rank;
     ta.nranks = cx.nranks;
     ta.rec = rec;
-    ta.mode = server ? 2 : (fused ? 0 : 1);
-    ta.done_ctas = done_ctas_d;
-    ta.step_flag = step_flag_d;
+    ta.mode = fused ? 0 : 1;
     ta.W = W;
     ta.idx_out = idx_d;
     ta.margins = margins_d;
@@ -1266,54 +1006,6 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     static const bool use_pdl = !(getenv("MOR_B200_DEIM_PDL") && getenv("MOR_B200_DEIM_PDL")[0] == '0');
     Timer t_total(MOR_T_TOTAL), t_panel(MOR_T_DEIM_PANEL), t_upd(MOR_T_DEIM_UPDATE);
     t_total.start();
-    struct SideEvents {
-        cudaEvent_t go = nullptr, done = nullptr;
-        ~SideEvents() {
-            if (go) cudaEventDestroy(go);
-            if (done) cudaEventDestroy(done);
-        }
-    } sev;
-    if (server) {
-        if (!cx.server_stream) {
-            int lo = 0, hi = 0;
-            MOR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            MOR_CUDA(cudaStreamCreateWithPriority(&cx.server_stream, cudaStreamNonBlocking, hi));
-        }
-        MOR_CUDA(cudaEventCreateWithFlags(&sev.go, cudaEventDisableTiming));
-        MOR_CUDA(cudaEventCreateWithFlags(&sev.done, cudaEventDisableTiming));
-        MOR_CUDA(cudaEventRecord(sev.go, cx.stream));                 // the state is zeroed
-        MOR_CUDA(cudaStreamWaitEvent(cx.server_stream, sev.go, 0));
-        ServerArgs sa{};
-        sa.k = (int)k;
-        sa.grid = grid;
-        sa.m = m;
-        sa.row_offset = row_offset;
-        sa.ld = ld;
-        sa.ldp = ldp;
-        sa.B = B;
-        sa.panel = panel.as<double>();
-        sa.R2 = R2;
-        sa.cands = cands.as<Cand>();
-        sa.done_ctas = done_ctas_d;
-        sa.step_flag = step_flag_d;
-        sa.ll = cx.box_ll;
-        for (int r = 0; r < cx.nranks; ++r) sa.peer_ll[r] = cx.peer_ll[r];
-        sa.rank = cx.rank;
-        sa.nranks = cx.nranks;
-        sa.seq0 = cx.deim_seq;
-        sa.idx_out = idx_d;
-        sa.margins = margins_d;
-        sa.values = values_d;
-        sa.csub = csub;
-        sa.Dsub = Dsub;
-        sa.bst = bst;
-        sa.status = status_d;
-        sa.tail_ns = tail_ns_d;
-        deim_server_kernel<<<1, DEIM_THREADS, 0, cx.server_stream>>>(sa);
-        MOR_CUDA(cudaGetLastError());
-        MOR_CUDA(cudaEventRecord(sev.done, cx.server_stream));
-        count_launch();
-    }
     for (int i = 0; i < (int)k; ++i) {
         const int l0 = blocked ? (i / DEIM_BLOCK) * DEIM_BLOCK : 0;   // first column of the current block
         const int j = i - l0;                                          // step inside the block
@@ -1340,7 +1032,6 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             t_panel.stop();
         }
         ta.i = i;
-        ta.need = (unsigned)i;
         ta.Pn = blocked && m > 0 ? Pn : nullptr;
         ta.ldn = ldn;
         ta.bw = bw;
@@ -1354,14 +1045,14 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
         const unsigned long long seq = cx.deim_seq + (unsigned long long)i;
         ta.slot = (int)(seq % DEIM_SLOTS);
         ta.tag = (unsigned)(seq % 0xfffffff0ull) + 1u;   // never 0 (a zeroed mailbox matches no step)
-        const bool pdl = use_pdl && blocked && fused && !server && j > 0;   // the stream's previous operation was a step kernel
+        const bool pdl = use_pdl && blocked && fused && j > 0;   // the stream's previous operation was a step kernel
         if (blocked && s0 > 0 && jj == 0) {
             // residuals of the next 4 panel columns in one pass over the s0 earlier ones, fused with this step's argmax
             MOR_CUDA(launch_step(deim_step4_kernel<R>, grid, cx.stream, pdl, Pn, m, ldn, s0, sw, (const double*)Dsub, R2, ldp,
                                  row_offset, ta));
         } else if (blocked) {
             MOR_CUDA(launch_step(deim_step_kernel<R, true>, grid, cx.stream, pdl, P2, m, ld2, jj,
-                                 (const double*)(server ? csub : sst + 3 * DEIM_SUB * DEIM_SUB), row_offset, ta));
+                                 (const double*)(sst + 3 * DEIM_SUB * DEIM_SUB), row_offset, ta));
         } else if (vec) {
             deim_step_kernel<R, true><<<grid, DEIM_THREADS, 0, cx.stream>>>(B, m, ld, i, c, row_offset, ta);
         } else {
@@ -1387,8 +1078,8 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             if (defer) MOR_CUDA(cudaStreamWaitEvent(cx.stream, col_ready[l1 / group_cols], 0));
             // W21 (bw x l0) and W12 (l1 x 16) sit back to back in one buffer: one launch, one all-reduce
             W12 = W21 + r16((size_t)bw * l0);
-            deim_gather_kernel<<<(bw * l0 + l1 * DEIM_BLOCK + 255) / 256, 256, 0, cx.stream>>>(
-                B, m, ld, row_offset, idx_d, l0, bw, bwn, W21, W12, server ? step_flag_d : nullptr, status_d);
+            deim_gather_kernel<<<(bw * l0 + l1 * DEIM_BLOCK + 255) / 256, 256, 0, cx.stream>>>(B, m, ld, row_offset, idx_d, l0, bw, bwn,
+                                                                                           W21, W12);
             if (cx.nranks > 1) MOR_TRY(comm_allreduce_sum(W21, r16((size_t)bw * l0) + (size_t)l1 * DEIM_BLOCK));
             deim_inv_f_kernel<<<l0 > 0 ? (l0 + DEIM_BLOCK - 1) / DEIM_BLOCK : 1, 256, 0, cx.stream>>>(A, W21, (int)k, l0, bw, bst, Sinv, Fm);
             if (l0 > 0) {
@@ -1401,7 +1092,6 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
             t_upd.stop();
         }
     }
-    if (server) MOR_CUDA(cudaStreamWaitEvent(cx.stream, sev.done, 0));   // the last steps' tails
     t_total.stop();
     if (cx.nranks > 1) cx.deim_seq += (unsigned long long)k;   // a one-rank (solo) call must not desynchronise the ranks' step counters
     MOR_CUDA(cudaGetLastError());
@@ -1425,8 +1115,7 @@ static int32_t deim_run(const double* B, int64_t m, int64_t k, int64_t ld, int64
     cx.timings[MOR_T_DEIM_EXCHANGE] = cx.nranks == 1 ? 0.0 : (fused ? 1.0 : 2.0);
     for (int64_t i = 0; i < k; ++i) idx_host[i] = (int64_t)idx_h[(size_t)i];
     if (status_h < 0) {
-        set_error(status_h == -1 ? "deim_interpolation_indices: the peer exchange timed out (a rank of the job did not reach the same greedy step)"
-                                 : "deim_interpolation_indices: the step kernels and the tail server lost each other (internal timeout)");
+        set_error("deim_interpolation_indices: the peer exchange timed out (a rank of the job did not reach the same greedy step)");
         return MOR_ERR_CUDA;
     }
     if (status_h != 0) {

@@ -43,7 +43,6 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;  // created by init
     cudaStream_t copy_stream = nullptr; // host->device ingest, overlapped with the first Gram pass; DEIM side stream
     cudaStream_t aux_stream = nullptr;  // DEIM host ingest: column groups upload while earlier panels are processed
-    cudaStream_t server_stream = nullptr;  // highest priority: the resident DEIM tail server must get its CTA slot first
     void* comm = nullptr;               // ncclComm_t
     int rank = 0, nranks = 1;
     double timings[MOR_T_NSLOTS] = {0};
