@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "modelorderreduction.jl_b200", "python"))
 
 M_FULL, N_COLS, K_MODES = 16 * 2**20, 1024, 64
 DEIM_M, DEIM_K = 16 * 2**20, 256
-TRAFFIC_RATIO_GRAM = 3.475   # ncu: 59.70 GB for 17.18 GB of operand at 2M rows (balanced schedule: tails re-read from HBM)
+TRAFFIC_RATIO_GRAM = 3.668   # ncu --set full (profiles/r02_ncu_full.txt): 63.01 GB for 17.18 GB of operand at 2M rows (balanced schedule: tails re-read from HBM)
 METRIC = "POD SVD() FP64 TFLOP/s at 16Mx1024 (algorithmic 2mn^2+2mnk flop / time); DEIM k=256 ms and HBM GB/s alongside"
 
 
@@ -825,8 +825,8 @@ def run_ours(args):
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                 "frac": panel_bytes / (deim_panel_ms * 1e-3) * 1e-9 / hbm_peak if deim_panel_ms > 0 else None,
                 "live_read_peak_gbs": pk_g.value,
-                # ncu --set full of the l0 = 128 panel launch at 16,777,216 rows: 19.327 GB read + 2.140 GB written
-                # for 21.475 GB algorithmic (profiles/r01_ncu_deim_blocked.txt): 1.000 x, summed over the launches
+                # ncu --set full of the l0 = 128 launch of the default deim_panel_kernel<256,16,5> at 16,777,216 rows:
+                # 19.327 GB read + 2.144 GB written for 21.475 GB algorithmic (profiles/r02_ncu_full.txt): 1.000 x
                 "traffic": 1.000 * panel_bytes,
                 "traffic_note": "ncu-measured 1.000 x algorithmic bytes (one launch), applied to all panel launches",
                 "bytes_per_rank": panel_bytes, "kernel_ms": deim_panel_ms,
@@ -909,7 +909,7 @@ def run_ours(args):
                                         "has no FP64 figure; nominal 37.2 TF at 1965 MHz)",
                          "frac": achieved / pk_t.value if pk_t.value else None,
                          # dram bytes of this kernel per launch from ncu --set full at 2,097,152 rows
-                         # (profiles/r01_ncu_final.txt), linear in the rows
+                         # (profiles/r02_ncu_full.txt), linear in the rows
                          "traffic": TRAFFIC_RATIO_GRAM * 8.0 * m_loc * n,
                          "traffic_note": f"ncu-measured {TRAFFIC_RATIO_GRAM:.3f} x (8 m n) bytes at 2M rows, scaled to this launch's rows",
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
