@@ -182,18 +182,22 @@ struct TailArgs {
 // One bordered (Doolittle) update of a small LU state by ONE warp: append row i (values w[0..dim)), then solve for
 // the coefficients of column i + 1.  The greedy choice is partial pivoting, so no row exchanges are needed and the
 // factorisation equals dgetrf's.  Z = inv(Uf) is kept explicitly: every phase is a set of independent dot products.
-template <int S>
-__device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, double* Z, double* c, int i, int dim,
-                                                     const double* w) {
+// S = row stride of the state.  Deliberately NOT inlined / unrolled and shared by the 16 x 16 and the 4 x 4 state:
+// the tail runs once per launch in one CTA with a cold instruction cache, so what it costs is the number of
+// instruction bytes fetched, not the number of instructions executed.
+__device__ __noinline__ void bordered_update_warp(double* Uf, double* L, double* Z, double* c, int S, int i, int dim,
+                                                  const double* w) {
     const int x = threadIdx.x & 31;
     if (x < i) {   // L row i:  ell[x] = sum_{t <= x} w[t] Z[t][x]
         double s = 0.0;
+#pragma unroll 1
         for (int t = 0; t <= x; ++t) s = fma(w[t], Z[t * S + x], s);
         L[i * S + x] = s;
     }
     __syncwarp();
     if (x >= i && x < dim) {   // U-factor row i:  Uf[i][x] = w[x] - sum_{t < i} ell[t] Uf[t][x]
         double s = 0.0;
+#pragma unroll 1
         for (int t = 0; t < i; ++t) s = fma(L[i * S + t], Uf[t * S + x], s);
         Uf[i * S + x] = w[x] - s;
     }
@@ -201,6 +205,7 @@ __device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, doub
     const double pivot = Uf[i * S + i];
     if (x < i) {   // Z column i:  Z[x][i] = -(sum_{t = x}^{i-1} Z[x][t] Uf[t][i]) / pivot
         double s = 0.0;
+#pragma unroll 1
         for (int t = x; t < i; ++t) s = fma(Z[x * S + t], Uf[t * S + i], s);
         Z[x * S + i] = -s / pivot;
     } else if (x == i) {
@@ -209,6 +214,7 @@ __device__ __forceinline__ void bordered_update_warp(double* Uf, double* L, doub
     __syncwarp();
     if (i + 1 < dim && x <= i) {   // c = Z[0:i+1, 0:i+1] * Uf[0:i+1, i+1]
         double s = 0.0;
+#pragma unroll 1
         for (int t = x; t <= i; ++t) s = fma(Z[x * S + t], Uf[t * S + i + 1], s);
         c[x] = s;
     }
@@ -246,12 +252,17 @@ __device__ void deim_tail_finish(const TailArgs& a, const double* wrec, TailSmem
     const int tid = threadIdx.x, k = a.krec;
     for (int jx = tid; jx < k; jx += DEIM_THREADS) a.W[(size_t)a.i * k + jx] = wrec[2 + jx];
     if (!a.blocked) return;
-    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK, SS = DEIM_SUB * DEIM_SUB;
+    constexpr int BB = DEIM_BLOCK * DEIM_BLOCK;
     double* bs = ts.st;
     double* ss = ts.st + BST_DOUBLES;
     const int warp = tid >> 5;
-    if (warp == 0) bordered_update_warp<DEIM_BLOCK>(bs, bs + BB, bs + 2 * BB, bs + 3 * BB, a.j, a.bw, wrec + 2 + k);
-    if (warp == 1) bordered_update_warp<DEIM_SUB>(ss, ss + SS, ss + 2 * SS, ss + 3 * SS, a.jj, a.sw, wrec + 2 + k + DEIM_BLOCK);
+    if (warp < 2) {   // warp 0: the panel's 16 x 16 state, warp 1: the sub-panel's 4 x 4 state -- one copy of the code
+        const bool big = warp == 0;
+        double* st = big ? bs : ss;
+        const int S = big ? DEIM_BLOCK : DEIM_SUB, SQ = S * S;
+        bordered_update_warp(st, st + SQ, st + 2 * SQ, st + 3 * SQ, S, big ? a.j : a.jj, big ? a.bw : a.sw,
+                             wrec + 2 + k + (big ? 0 : DEIM_BLOCK));
+    }
     __syncthreads();
     // the pivot is the residual at the chosen row: exactly zero <=> P'U singular (SingularException in the reference)
     if (tid == 0 && bs[a.j * DEIM_BLOCK + a.j] == 0.0 && !a.last && *a.status == 0) *a.status = a.i + 1;
@@ -289,14 +300,24 @@ __device__ void deim_tail(const TailArgs& a, double* sbuf, double* sv, long long
     }
     deim_prefetch_state(a, ts);
     // (a) this rank's winner over the per-CTA candidates of the launch
+    // all loads first (independent L2 round trips), then the merges
+    constexpr int PER = 5;   // covers grids up to 1280 CTAs in one round
+    double cv[PER], c2[PER];
+    long long ci[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int t = tid + u * DEIM_THREADS;
+        const bool in = t < (int)gridDim.x;
+        cv[u] = in ? __ldcg(&a.cands[t].val) : -1.0;
+        ci[u] = in ? __ldcg(&a.cands[t].idx) : MOR_IDX_NONE;
+        c2[u] = in ? __ldcg(&a.cands[t].val2) : -1.0;
+    }
     double bv = -1.0, b2 = -1.0;
     long long bi = MOR_IDX_NONE;
-    for (int t = tid; t < (int)gridDim.x; t += DEIM_THREADS) {
-        const double v = __ldcg(&a.cands[t].val);
-        const long long ix = __ldcg(&a.cands[t].idx);
-        const double s = __ldcg(&a.cands[t].val2);
-        cand_merge(bv, bi, b2, v, ix, s);
-    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) cand_merge(bv, bi, b2, cv[u], ci[u], c2[u]);
+    for (int t = tid + PER * DEIM_THREADS; t < (int)gridDim.x; t += DEIM_THREADS)
+        cand_merge(bv, bi, b2, __ldcg(&a.cands[t].val), __ldcg(&a.cands[t].idx), __ldcg(&a.cands[t].val2));
     __syncthreads();   // sv/si/ss2 were used by the CTA's own reduction
     cand_block_reduce(bv, bi, b2, sv, si, ss2);
     if (tid == 0) {
