@@ -300,6 +300,70 @@ def single_process_leg(args, world, lib, s_multi, idx_control):
     return out
 
 
+def next_rows_section(args, lib, B, idx, md_loc, r0d, Md, world, hbm_peak, dmma_peak):
+    """f1: the DEIM projector ((U[idx,:])' \\ (U'V))' (deim.jl:150) on the resident 16M x 256 DEIM basis and a 16M x 64
+    POD-like basis -- its cost is the U'V contraction.  f2 (one GPU): the Galerkin projection V'AV (deim.jl:154) of a
+    sparse MOL operator (5-point Laplacian on a 2048 x 2048 grid, Julia CSC arrays) through the host-pointer entry."""
+    import numpy as np
+    from mor_b200 import _lib
+    from mor_b200.device import DeviceMatrix, orthonormalize_dev
+    out = {}
+    kd, kp = DEIM_K, K_MODES
+    Vp = DeviceMatrix.alloc(md_loc, kp).synth(_lib.SYNTH_GAUSS, seed=11, global_row0=r0d, param=1.0 / math.sqrt(Md))
+    orthonormalize_dev(Vp)
+    P = DeviceMatrix.alloc(kp, kd)
+    idx64 = np.ascontiguousarray(idx, dtype=np.int64)
+    best, best_proj = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _lib.check(lib.mor_b200_deim_projector_dev(B.handle, Vp.handle, idx64.ctypes.data, P.handle))
+        dt = (time.perf_counter() - t0) * 1e3
+        if best is None or dt < best:
+            best, best_proj = dt, _lib.last_timings()["proj"]
+    fl = 2.0 * md_loc * kd * kp
+    by = 8.0 * md_loc * (kd + kp)
+    out["f1_deim_projector"] = {"reference": "deim.jl:150", "shape": f"U {Md}x{kd}, V {Md}x{kp}", "ms": best,
+                                "contraction_ms": best_proj, "contraction_tflops": fl / (best_proj * 1e-3) * 1e-12,
+                                "contraction_frac_of_dmma_peak": fl / (best_proj * 1e-3) * 1e-12 / dmma_peak if dmma_peak else None,
+                                "contraction_gbs": by / (best_proj * 1e-3) * 1e-9, "frac_of_hbm_peak": by / (best_proj * 1e-3) * 1e-9 / hbm_peak,
+                                "projector_finite": bool(np.isfinite(P.to_host()).all())}
+    Vp.free(); P.free()
+    if world == 1:
+        import scipy.sparse as sp
+        nx = 2048
+        m = nx * nx
+        e = np.ones(nx)
+        T = sp.diags([e[:-1], -2.0 * e, e[:-1]], [-1, 0, 1], format="csc")
+        A = (sp.kron(sp.identity(nx, format="csc"), T) + sp.kron(T, sp.identity(nx, format="csc"))).tocsc()
+        A.sort_indices()
+        colptr = (A.indptr.astype(np.int64) + 1)
+        rowval = (A.indices.astype(np.int64) + 1)
+        nzval = np.ascontiguousarray(A.data, dtype=np.float64)
+        k = K_MODES
+        Vd = DeviceMatrix.alloc(m, k).synth(_lib.SYNTH_GAUSS, seed=12, global_row0=0, param=1.0 / math.sqrt(m))
+        orthonormalize_dev(Vd)
+        Vh = Vd.to_host()
+        Vd.free()
+        Ahat = np.empty((k, k), order="F")
+        best, tim = None, None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _lib.check(lib.mor_b200_galerkin_csc(m, colptr.ctypes.data, rowval.ctypes.data, nzval.ctypes.data, Vh.ctypes.data, k, m,
+                                                 Ahat.ctypes.data, k))
+            dt = (time.perf_counter() - t0) * 1e3
+            if best is None or dt < best:
+                best, tim = dt, _lib.last_timings()
+        ref = Vh[:, :4].T @ (A @ Vh[:, :4])
+        by = 16.0 * A.nnz + 8.0 * (m + 1) + 2 * 8.0 * m * k
+        out["f2_galerkin_projection"] = {"reference": "deim.jl:154", "operator": f"5-point Laplacian on a {nx}x{nx} grid: m={m}, nnz={A.nnz}", "k": k,
+                                          "e2e_ms_host_pointers": best, "h2d_ms": tim["h2d"], "spmm_ms": tim["spmm"], "contraction_ms": tim["proj"],
+                                          "spmm_algorithmic_gbs": by / (tim["spmm"] * 1e-3) * 1e-9,
+                                          "spmm_frac_of_hbm_peak": by / (tim["spmm"] * 1e-3) * 1e-9 / hbm_peak,
+                                          "spmm_bytes_note": "16 nnz (index + value) + 8 (m+1) + V read once + W written once",
+                                          "max_abs_err_vs_scipy_4x4_block": float(np.max(np.abs(Ahat[:4, :4] - ref)))}
+    return out
+
+
 def deim_independent_check(torch, dist, bt, m_loc, row0, idx, world, steps, lib_values=None):
     """Full-size check of the chosen DEIM points by an independent code path (torch fp64: cuSOLVER LU solve +
     cuBLAS gemv on the aliased basis; none of the library's kernels): for every checked greedy step l the
@@ -856,6 +920,15 @@ def run_ours(args):
             "tail_note": "tail = per-step reduction + peer exchange + small LU updates, fused into the step kernels (timed "
                          "inside the kernel); update = per-panel coefficient and inverse-update launches",
             "e2e": deim_e2e}
+    # ---- the "next" rows of SURVEY 8f, measured on the same basis (never fatal for the bench line) --------------------
+    next_rows = None
+    if not args.no_next_rows:
+        try:
+            next_rows = next_rows_section(args, lib, B, idx, md_loc, r0d, Md, world, hbm_peak, pk_t.value)
+        except Exception as ex:
+            next_rows = {"error": repr(ex)}
+            if world > 1:
+                raise
     B.free()
     single = None
     if world > 1:
@@ -913,7 +986,7 @@ def run_ours(args):
                          "traffic": TRAFFIC_RATIO_GRAM * 8.0 * m_loc * n,
                          "traffic_note": f"ncu-measured {TRAFFIC_RATIO_GRAM:.3f} x (8 m n) bytes at 2M rows, scaled to this launch's rows",
                          "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_ms},
-            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "single_process": single,
+            "pod_breakdown_ms": parts, "checks": checks, "deim": deim, "rsvd": rsvd, "kat": kat, "next_rows": next_rows, "single_process": single,
             "cpu_baseline": cpu}
     emit(line)
 
@@ -944,6 +1017,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the projector / Galerkin-projection lines (SURVEY 8f)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory e2e leg")
     ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the single-process multi-GPU leg on rank 0")
     ap.add_argument("--no-rsvd", action="store_true")

@@ -155,7 +155,9 @@ int32_t mor_b200_deim_projector(const double* U, int64_t m, int64_t kd, int64_t 
 
 /* Galerkin projection of the linear part, deim.jl:154-155,261.
  * A_hat (k x k, ld = lda) = V' * A * V with A an m x m Julia SparseMatrixCSC given by its own arrays
- * (colptr m+1 entries, rowval / nzval nnz entries, 1-based Int64 indices); single rank. */
+ * (colptr m+1 entries, rowval / nzval nnz entries, 1-based Int64 indices).  One process per GPU: single rank.
+ * Single-process multi-GPU mode: the columns of A are sharded over the GPUs (each takes the rows of V its columns
+ * touch straight from the caller's host matrix), the k x k partial products are all-reduced. */
 int32_t mor_b200_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                               const double* V, int64_t k, int64_t ldv, double* Ahat, int64_t lda);
 /* out (k x nvec, ld = ldo) = V' * Xv: g_hat = V' * g and y_hat(0) = V' * snapshot[:, 1].  V (m x k) and
@@ -214,7 +216,9 @@ int32_t mor_b200_deim_projector_dev(mor_mat_t U, mor_mat_t V, const int64_t* idx
 #define MOR_T_DEIM_FALLBACK 14 /* not a time: 1 if a near-tie made the last DEIM call repeat on the streaming path */
 #define MOR_T_DEIM_EXCHANGE 15 /* not a time: per-step candidate exchange of the last DEIM call: 0 single rank,
                                   1 peer mailboxes over NVLink (stores + flags inside the step kernel), 2 ncclAllGather */
-#define MOR_T_NSLOTS 16
+#define MOR_T_SPMM 16      /* Galerkin projection: the sparse A'V kernel                */
+#define MOR_T_PROJ 17      /* Galerkin projection / projector: the dense W'V contraction */
+#define MOR_T_NSLOTS 24
 int32_t mor_b200_last_timings(double* ms, int32_t n);
 /* number of kernel launches issued by the library since the last reset (this rank) */
 int64_t mor_b200_launch_count(int32_t reset);

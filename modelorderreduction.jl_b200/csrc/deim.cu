@@ -1199,7 +1199,11 @@ int32_t deim_projector_device(const double* U, int64_t m, int kd, int64_t ldu, c
     MOR_TRY(d_fail.alloc(sizeof(int)));
     std::vector<long long> idx_ll(idx_host, idx_host + kd);
     MOR_CUDA(cudaMemcpyAsync(d_idx.p, idx_ll.data(), sizeof(long long) * (size_t)kd, cudaMemcpyHostToDevice, cx.stream));
+    for (double& t : cx.timings) t = 0.0;
+    Timer t_proj(MOR_T_PROJ);
+    t_proj.start();
     MOR_TRY(gemm_tn(U, ldu, kd, V, ldv, kp, m, UtV.as<double>(), kd));
+    t_proj.stop();
     MOR_TRY(gather_rows(U, m, ldu, row_offset, d_idx.as<long long>(), kd, PtU.as<double>(), kd));
     if (cx.nranks > 1) {
         MOR_TRY(comm_allreduce_sum(UtV.as<double>(), (size_t)kd * kp));
@@ -1210,6 +1214,7 @@ int32_t deim_projector_device(const double* U, int64_t m, int kd, int64_t ldu, c
     int fail = 0;
     MOR_CUDA(cudaMemcpyAsync(&fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
     MOR_CUDA(cudaStreamSynchronize(cx.stream));
+    t_proj.collect();
     if (fail != 0) {
         set_error("deim_projector: U[indices, :] is exactly singular (SingularException in the reference)");
         return MOR_ERR_SINGULAR;

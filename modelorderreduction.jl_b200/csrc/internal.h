@@ -134,6 +134,10 @@ int32_t multi_pod_free(mor_pod_s* h);
 int32_t multi_deim_indices(const double* B, int64_t m, int64_t k, int64_t ldb, int64_t* idx_out);
 int32_t multi_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu, const double* V, int64_t kp, int64_t ldv,
                              const int64_t* idx, double* P_out, int64_t ldp);
+int32_t multi_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* V,
+                           int64_t k, int64_t ldv, double* Ahat, int64_t lda);
+int32_t galerkin_csc_slice(int64_t ncols, const int64_t* colptr, const int64_t* rowval, const double* nzval, int64_t row_lo,
+                           int64_t nrows, int64_t c_off, const double* V, int64_t k, int64_t ldv, double* Ahat_dev);
 int32_t multi_project(const double* V, int64_t m, int64_t k, int64_t ldv, const double* Xv, int64_t nvec, int64_t ldx,
                       double* out, int64_t ldo);
 // entry points that only make sense on one device (device-resident API, single-rank helpers): in multi mode GPU 0

@@ -12,6 +12,7 @@
 //
 // Entry points that are per-device by nature (the device-resident API, the single-rank sparse Galerkin product) and
 // inputs that do not shard (a wide snapshot matrix, tiny problems) run on GPU 0 as a one-rank job ("solo").
+#include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -363,6 +364,42 @@ int32_t multi_deim_projector(const double* U, int64_t m, int64_t kd, int64_t ldu
         multi_shard(m, r, &row0, &rows);
         return mor_b200_deim_projector(U + row0, rows, kd, ldu, V + row0, kp, ldv, idx, r == 0 ? P_out : P[(size_t)r].data(),
                                        r == 0 ? ldp : kp);
+    });
+}
+
+// V' A V with the COLUMNS of A sharded: GPU r takes columns [c0, c1) of the CSC arrays and the rows [lo, hi) of V that
+// those columns touch (for a stencil / MOL operator: its own rows plus a halo of the stencil width) straight from the
+// caller's host matrix -- the halo needs no inter-GPU exchange because V lives on the host -- forms
+// W_r = A[:, c0:c1]' V and the partial product W_r' V[c0:c1, :]; the k x k partials are all-reduced.
+int32_t multi_galerkin_csc(int64_t m, const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* V,
+                           int64_t k, int64_t ldv, double* Ahat, int64_t lda) {
+    MOR_ARG(colptr && V && Ahat && m >= 1 && k >= 1 && ldv >= m && lda >= k, "mor_b200_galerkin_csc: bad arguments");
+    MOR_ARG(colptr[0] == 1 && colptr[m] >= 1, "mor_b200_galerkin_csc: colptr must be 1-based (Julia SparseMatrixCSC)");
+    const int64_t nnz = colptr[m] - 1;
+    MOR_ARG(nnz == 0 || (rowval && nzval), "mor_b200_galerkin_csc: null rowval / nzval");
+    if (m < (int64_t)8192 * g_multi.n)
+        return multi_solo([&]() -> int32_t { return mor_b200_galerkin_csc(m, colptr, rowval, nzval, V, k, ldv, Ahat, lda); });
+    return multi_all([&](int r) -> int32_t {
+        int64_t c0, nc;
+        multi_shard(m, r, &c0, &nc);
+        // rows of V this slice touches: its own rows (for the final contraction) and whatever its columns reference
+        int64_t lo = c0, hi = c0 + nc;
+        for (int64_t p = colptr[c0] - 1; p < colptr[c0 + nc] - 1; ++p) {
+            const int64_t row = rowval[p] - 1;
+            MOR_ARG(row >= 0 && row < m, "galerkin projection: row index outside 1..m in the CSC structure");
+            lo = std::min(lo, row);
+            hi = std::max(hi, row + 1);
+        }
+        Ctx& cx = ctx();
+        DevBuf dA;
+        MOR_TRY(dA.alloc(sizeof(double) * (size_t)k * k));
+        MOR_TRY(galerkin_csc_slice(nc, colptr + c0, rowval, nzval, lo, hi - lo, c0 - lo, V, k, ldv, dA.as<double>()));
+        MOR_TRY(comm_allreduce_sum(dA.as<double>(), (size_t)k * k));
+        if (r == 0)
+            MOR_CUDA(cudaMemcpy2DAsync(Ahat, (size_t)lda * 8, dA.p, (size_t)k * 8, (size_t)k * 8, (size_t)k, cudaMemcpyDeviceToHost,
+                                       cx.stream));
+        MOR_CUDA(cudaStreamSynchronize(cx.stream));
+        return MOR_OK;
     });
 }
 

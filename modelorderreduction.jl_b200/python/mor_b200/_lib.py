@@ -16,8 +16,8 @@ MOR_SVD, MOR_TSVD, MOR_RSVD = 0, 1, 2
 SYNTH_GRADED, SYNTH_GAUSS, SYNTH_LOWRANK, SYNTH_KAT, SYNTH_BURGERS = 0, 1, 2, 3, 4
 POD_MAY_OVERWRITE, POD_FORCE_TWO_PASS = 1, 2
 T_SLOTS = ("total", "h2d", "gram", "apply", "core", "basis", "comm", "deim_step", "deim_tail",
-           "d2h", "sketch", "deim_panel", "deim_blocked", "deim_update", "deim_fallback", "deim_exchange")
-T_NSLOTS = 16
+           "d2h", "sketch", "deim_panel", "deim_blocked", "deim_update", "deim_fallback", "deim_exchange", "spmm", "proj")
+T_NSLOTS = 24
 
 
 class MorError(RuntimeError):

@@ -95,7 +95,18 @@ def main():
     assert np.max(np.abs(P - Pref)) <= 1e-10 * np.max(np.abs(Pref))
     g = rng.standard_normal(131_072)
     assert np.max(np.abs(mor_b200.project(V, g) - V.T @ g)) <= 1e-12 * np.linalg.norm(g)
-    print(f"DEIM (k=256, peer-mailbox exchange inside one process), projector, projections ok on {n_gpus} GPU(s)", flush=True)
+    # Galerkin projection V'AV of a sparse MOL operator: the COLUMNS of A are sharded, every GPU takes the rows of V its
+    # columns touch from the host matrix (stencil halo), the k x k partials are all-reduced (deim.jl:154)
+    import scipy.sparse as sp
+    mg = 131_072
+    A = (sp.diags([np.full(mg - 1, 1.0), np.full(mg, -2.0), np.full(mg - 1, 1.0), np.full(mg - 512, 0.5), np.full(mg - 512, 0.5)],
+                  [-1, 0, 1, -512, 512], format="csc")
+         + sp.coo_matrix((rng.standard_normal(2000), (rng.integers(0, mg, 2000), rng.integers(0, mg, 2000))), shape=(mg, mg)).tocsc())
+    Ah = mor_b200.galerkin_project(A, V)
+    ref = V.T @ (A @ V)
+    assert np.max(np.abs(Ah - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1.0)
+    assert _lib.last_timings()["spmm"] > 0
+    print(f"DEIM (k=256, peer-mailbox exchange inside one process), projector, projections, sharded Galerkin product ok on {n_gpus} GPU(s)", flush=True)
 
     # ---- device API = GPU 0; shutdown; back to the one-GPU mode -----------------------------------------
     B = DeviceMatrix.alloc(50_000, 24).synth(_lib.SYNTH_GAUSS, seed=5, param=0.01)
