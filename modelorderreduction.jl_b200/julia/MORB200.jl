@@ -154,7 +154,6 @@ release!(f::Factor) = finalize(f)
 
 const Snaps = Union{F64Mat, F64VoV}
 
-struct NotConverged <: Exception end
 function factor_or_nothing(args...; kw...)
     try
         return factor(args...; kw...)

@@ -7,11 +7,16 @@ TEST INFRASTRUCTURE ONLY.  This module is the checker, never the product: only
 
 PARITY UNPINNED BY THE REFERENCE: Julia is not installed in the build image and the
 reference's tests (``test/interface.jl``, ``test/DataReduction.jl``, ``test/deim.jl``)
-assert only shapes and ranges on this path, never a numeric value.
+assert only shapes and ranges on this path, never a numeric value,
+so no output of the reference itself can serve as a golden vector.
 The oracle is therefore pinned against (i) the analytic answers of the reference's own
 fixtures (``[3 0;0 1]``: s=[3,1], renergy .75/.5), (ii) the reference's range assertions,
-and (iii) the LAPACK routines Julia itself dispatches to (``dgesdd``, ``dgetrf/dgetrs``,
-``dgemv``), called here through scipy's OpenBLAS.
+(iii) the LAPACK routines Julia itself dispatches to (``dgesdd``, ``dgetrf/dgetrs``,
+``dgemv``), called here through scipy's OpenBLAS, and (iv) an independent 50-digit pin
+that uses no LAPACK/BLAS at all: ``oracle/make_golden_mpmath.py`` ->
+``tests/golden/mpmath_golden.json`` (singular values / energies / left vectors of the
+reference's ``sin(i*j/n)`` fixture, DEIM chains of deim.jl:13-24 with the margin by which
+every argmax is decided), checked in ``tests/test_oracle.py``.
 
 Every function cites the reference lines it restates (paths relative to /root/reference).
 Indices returned by :func:`deim_interpolation_indices` are 1-based, like Julia's.
