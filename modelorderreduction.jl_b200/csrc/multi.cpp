@@ -40,7 +40,9 @@ struct Multi {
     std::vector<std::unique_ptr<Worker>> w;
     bool env_checked = false;
 };
-Multi g_multi;
+// Leaked on purpose: a process that exits without mor_b200_shutdown (a Julia session) must not run ~thread on the
+// still-joinable worker threads during static destruction (std::terminate).
+Multi& g_multi = *new Multi;
 thread_local bool tl_worker = false;
 
 void worker_main(int r, Worker* w) {
