@@ -267,6 +267,8 @@ struct SmallInfo {
     int chol_fail;   // 1-based index of the first non-positive pivot, 0 = ok
     int rotations;   // Jacobi rotations applied in the last sweep
     double max_cos;  // largest |cosine| between two columns met in the last sweep
+    int sync_fail;   // Jacobi: a block-version wait timed out (never expected; reported instead of hanging)
+    int pad_;
 };
 int32_t small_info_reset(SmallInfo* d_info);
 int32_t small_info_read(const SmallInfo* d_info, SmallInfo* h);

@@ -345,20 +345,203 @@ jacobi_block_sweep_kernel(double* __restrict__ A, int lda, int rows, int n, int 
     }
 }
 
-int32_t launch_block_sweep(double* A, int lda, int rows, int n, double tol, SmallInfo* d_info) {
+// ---- blocked sweep, Gram form ------------------------------------------------------------------------------------
+// Same tournament, same rotations, one block-wide reduction per round instead of four.  The four steps of
+// jacobi_block_sweep_kernel each need the three dot products of four column pairs: reduce -> barrier -> rotate, four
+// times in a row.  Here the whole 8 x 8 Gram matrix G = C'C of the block pair (36 dot products) is reduced ONCE; every
+// warp then runs the same rotation sequence on its own copy of G in shared memory -- a rotation of columns (u, v) acts
+// on G as G <- R'GR, so the later steps of the round see exactly the dot products they would recompute -- accumulates
+// the 8 x 8 orthogonal J = R1 R2 ..., and each thread applies J to the 8 x 4 values it holds (C <- C J).  The round's
+// dependent chain shrinks from 4 x (reduce + barrier + sqrt/div chain) to 1 reduce + barrier + 4 short chains.
+// Rounding: the entries of G are updated algebraically inside a round (errors of a few eps relative to |a_u||a_v|,
+// far below the rotation threshold rows * eps) and recomputed from the columns in the next round.
+__global__ void __launch_bounds__(ST, 1)
+jacobi_block_sweep_gram_kernel(double* __restrict__ A, int lda, int rows, int n, int nblk_even, double tol,
+                               SmallInfo* __restrict__ info, int* __restrict__ ver, int epoch_base) {
+    // No grid barrier between the rounds: a block pair only depends on the two CTAs that held its blocks in the
+    // previous round.  ver[X] counts the rounds block X has been through (monotone over the whole SVD); the owner of
+    // a round publishes it (release) after its stores, the next owner waits for it (acquire).  The launch stays
+    // cooperative so that all CTAs are co-resident and the waits cannot deadlock.
+    __shared__ double part[ST / 32][36];
+    __shared__ double Gw[ST / 32][64], Jw[ST / 32][64], Tw[ST / 32][64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N1 = nblk_even - 1, npairs = nblk_even / 2;
+    int my_rot = 0;
+    double my_maxcos = 0.0;
+    double* G = Gw[warp];
+    double* J = Jw[warp];
+    double* T = Tw[warp];
+    for (int round = 0; round < N1; ++round) {
+        for (int b = blockIdx.x; b < npairs; b += gridDim.x) {
+            int I, Jb;
+            pair_of(b, round, N1, I, Jb);
+            const int need = epoch_base + round;
+            if (tid < 2) {   // both blocks have been through the previous round
+                const int* vp = ver + (tid == 0 ? I : Jb);
+                const long long t0 = clock64();
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(vp) : "memory");
+                    if (seen < need && clock64() - t0 > (1LL << 30)) {   // ~0.5 s: report, never hang
+                        atomicExch(&info->sync_fail, 1);
+                        break;
+                    }
+                } while (seen < need);
+            }
+            __syncthreads();
+            double c[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = (j < BC ? I * BC + j : Jb * BC + (j - BC));
+                const double* src = A + (size_t)col * lda;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = tid + i * ST;
+                    c[j][i] = (col < n && r < rows) ? __ldcg(src + r) : 0.0;
+                }
+            }
+            // the 36 dot products of the 8 columns, reduced over the CTA in one go
+            {
+                double g[36];
+                int e = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int v = u; v < 8; ++v) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sacc = fma(c[u][i], c[v][i], sacc);
+                        g[e++] = sacc;
+                    }
+#pragma unroll
+                for (int t = 0; t < 36; ++t) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) g[t] += __shfl_xor_sync(0xffffffffu, g[t], off);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < 36; ++t) part[warp][t] = g[t];
+                }
+            }
+            __syncthreads();
+            // every warp builds its own copy of G (and J = I) and runs the same rotation sequence on it
+            for (int t = lane; t < 36; t += 32) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int w = 0; w < ST / 32; ++w) sacc += part[w][t];
+                // unpack the upper-triangle index t -> (u, v)
+                int u = 0, rem = t;
+                while (rem >= 8 - u) {
+                    rem -= 8 - u;
+                    ++u;
+                }
+                const int v = u + rem;
+                G[u * 8 + v] = sacc;
+                G[v * 8 + u] = sacc;
+            }
+            J[lane] = (lane >> 3) == (lane & 7) ? 1.0 : 0.0;
+            J[lane + 32] = ((lane + 32) >> 3) == (lane & 7) ? 1.0 : 0.0;
+            __syncwarp();
+            bool any_rot = false;
+            const int first = round == 0 ? 0 : 3;   // sequence 4, 5, 6 (pairs inside the two blocks, once per sweep), then 0, 1, 2, 3
+            for (int q = first; q < 7; ++q) {
+                const int S = q < 3 ? q + 4 : q - 3;
+                const int k = lane & 3, i8 = lane >> 2;
+                const int u = kSteps[S].u[k], v = kSteps[S].v[k];
+                double cs = 1.0, sn = 0.0;
+                {
+                    const double a = G[u * 8 + u], bb = G[v * 8 + v], cc = G[u * 8 + v];
+                    const double denom = sqrt(a) * sqrt(bb);
+                    if (fabs(cc) > tol * denom) {
+                        const double zeta = (bb - a) / (2.0 * cc);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        cs = rsqrt(1.0 + t * t);
+                        sn = cs * t;
+                        if (tid < 4) {
+                            ++my_rot;
+                            my_maxcos = fmax(my_maxcos, fabs(cc) / denom);
+                        }
+                    }
+                }
+                // (all lanes with the same k computed the same (cs, sn): no broadcast needed)
+                if (__ballot_sync(0xffffffffu, sn != 0.0) == 0u) continue;
+                any_rot = true;
+                // T = G R (columns u, v of row i8), J <- J R
+                {
+                    const double gu = G[i8 * 8 + u], gv = G[i8 * 8 + v];
+                    T[i8 * 8 + u] = cs * gu - sn * gv;
+                    T[i8 * 8 + v] = sn * gu + cs * gv;
+                    const double ju = J[i8 * 8 + u], jv = J[i8 * 8 + v];
+                    J[i8 * 8 + u] = cs * ju - sn * jv;
+                    J[i8 * 8 + v] = sn * ju + cs * jv;
+                }
+                __syncwarp();
+                // G = R' T (rows u, v of column i8)
+                {
+                    const double tu = T[u * 8 + i8], tv = T[v * 8 + i8];
+                    G[u * 8 + i8] = cs * tu - sn * tv;
+                    G[v * 8 + i8] = sn * tu + cs * tv;
+                }
+                __syncwarp();
+            }
+            if (any_rot) {   // C <- C J on the 8 x 4 values of this thread
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double x[8];
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) x[h] = c[h][i];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) sacc = fma(x[h], J[h * 8 + j], sacc);
+                        c[j][i] = sacc;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = (j < BC ? I * BC + j : Jb * BC + (j - BC));
+                    double* dst = A + (size_t)col * lda;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = tid + i * ST;
+                        if (col < n && r < rows) __stcg(dst + r, c[j][i]);
+                    }
+                }
+            }
+            __threadfence();  // this thread's column stores, before the versions are published
+            __syncthreads();  // (part[] is also reused by the next block pair of this CTA)
+            if (tid < 2) {
+                int* vp = ver + (tid == 0 ? I : Jb);
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(vp), "r"(need + 1) : "memory");
+            }
+        }
+    }
+    if (tid < 4 && my_rot > 0) {
+        atomicAdd(&info->rotations, my_rot);
+        atomicMax(reinterpret_cast<unsigned long long*>(&info->max_cos), (unsigned long long)__double_as_longlong(my_maxcos));
+    }
+}
+
+int32_t launch_block_sweep(double* A, int lda, int rows, int n, double tol, SmallInfo* d_info, int* d_ver, int sweep) {
     Ctx& cx = ctx();
     const int nblk = (n + BC - 1) / BC;
     int nblk_even = (nblk + 1) & ~1;
+    // the Gram form of the round (one block-wide reduction instead of four); MOR_B200_JACOBI_GRAM=0: the four-step form
+    static const bool gram_form = !(getenv("MOR_B200_JACOBI_GRAM") && getenv("MOR_B200_JACOBI_GRAM")[0] == '0');
+    void* kern = gram_form ? (void*)jacobi_block_sweep_gram_kernel : (void*)jacobi_block_sweep_kernel;
     int per_sm = 0;
-    MOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_sweep_kernel, ST, 0));
+    if (gram_form) MOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_sweep_gram_kernel, ST, 0));
+    else MOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_sweep_kernel, ST, 0));
     if (per_sm < 1) {
         set_error("jacobi_block_sweep_kernel cannot be made resident");
         return MOR_ERR_CUDA;
     }
     int grid = nblk_even / 2;
     if (grid > per_sm * cx.num_sms) grid = per_sm * cx.num_sms;
-    void* args[] = {&A, &lda, &rows, &n, &nblk_even, &tol, &d_info};
-    MOR_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_block_sweep_kernel, dim3(grid), dim3(ST), args, 0, cx.stream));
+    int epoch_base = sweep * (nblk_even - 1);   // every block goes through nblk_even - 1 rounds per sweep
+    void* args[] = {&A, &lda, &rows, &n, &nblk_even, &tol, &d_info, &d_ver, &epoch_base};
+    MOR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(ST), args, 0, cx.stream));
     count_launch();
     return MOR_OK;
 }
@@ -432,6 +615,9 @@ int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std:
     MOR_TRY(info_buf.alloc(sizeof(SmallInfo)));
     MOR_TRY(norms.alloc(sizeof(double) * (size_t)n));
     SmallInfo* d_info = info_buf.as<SmallInfo>();
+    DevBuf ver_buf;   // block versions of the barrier-free blocked sweep
+    MOR_TRY(ver_buf.alloc(sizeof(int) * (size_t)(n / BC + 4)));
+    MOR_CUDA(cudaMemsetAsync(ver_buf.p, 0, ver_buf.bytes, cx.stream));
     if (V) MOR_TRY(small_identity(V, n, ldv));
     const int n_even = (n + 1) & ~1;
     // rotate while |cos(a_p, a_q)| > tol.  dgesvj uses sqrt(rows)*eps; the computed dot product of a
@@ -446,12 +632,16 @@ int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std:
     while (!converged && sweeps < max_sweeps) {
         MOR_TRY(small_info_reset(d_info));
         const int big = rows > n ? rows : n;
-        if (V == nullptr && rows <= 4 * ST && n >= 16) MOR_TRY(launch_block_sweep(A, lda, rows, n, tol, d_info));
+        if (V == nullptr && rows <= 4 * ST && n >= 16) MOR_TRY(launch_block_sweep(A, lda, rows, n, tol, d_info, ver_buf.as<int>(), sweeps));
         else if (big <= 4 * ST) MOR_TRY(launch_sweep<4>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));
         else if (big <= 16 * ST) MOR_TRY(launch_sweep<16>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));
         else MOR_TRY(launch_sweep<0>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));
         SmallInfo h;
         MOR_TRY(small_info_read(d_info, &h));
+        if (h.sync_fail) {
+            set_error("Jacobi SVD: a block-version wait of the barrier-free sweep timed out");
+            return MOR_ERR_CUDA;
+        }
         ++sweeps;
         if (getenv("MOR_B200_DEBUG"))
             fprintf(stderr, "[mor_b200]     jacobi sweep %d: %d rotations, max cosine %.3e\n", sweeps, h.rotations, h.max_cos);
