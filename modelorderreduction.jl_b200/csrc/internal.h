@@ -295,8 +295,10 @@ int32_t col_norms(const double* A, int lda, int rows, int n, std::vector<double>
 // One-sided Jacobi on the columns of A (rows x n, lda), in place: on return the columns are
 // mutually orthogonal (A_in * V = A_out, V n x n accumulated if non-null).  sigma = column
 // norms sorted descending, order[j] = column holding the j-th largest.
+// well_scaled: A is a row / column scaling of a well-conditioned matrix (lets the blocked sweep use its faster
+// Gram-form round; see jacobi.cu)
 int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std::vector<double>& sigma,
-                   std::vector<int>& order, int* sweeps_out);
+                   std::vector<int>& order, int* sweeps_out, bool well_scaled = false);
 
 // ---- POD driver (pod.cu) ---------------------------------------------------------------------
 }  // namespace mor

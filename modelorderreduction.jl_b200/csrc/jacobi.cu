@@ -523,12 +523,11 @@ jacobi_block_sweep_gram_kernel(double* __restrict__ A, int lda, int rows, int n,
     }
 }
 
-int32_t launch_block_sweep(double* A, int lda, int rows, int n, double tol, SmallInfo* d_info, int* d_ver, int sweep) {
+int32_t launch_block_sweep(double* A, int lda, int rows, int n, double tol, SmallInfo* d_info, int* d_ver, int sweep,
+                           bool gram_form) {
     Ctx& cx = ctx();
     const int nblk = (n + BC - 1) / BC;
     int nblk_even = (nblk + 1) & ~1;
-    // the Gram form of the round (one block-wide reduction instead of four); MOR_B200_JACOBI_GRAM=0: the four-step form
-    static const bool gram_form = !(getenv("MOR_B200_JACOBI_GRAM") && getenv("MOR_B200_JACOBI_GRAM")[0] == '0');
     void* kern = gram_form ? (void*)jacobi_block_sweep_gram_kernel : (void*)jacobi_block_sweep_kernel;
     int per_sm = 0;
     if (gram_form) MOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_sweep_gram_kernel, ST, 0));
@@ -608,7 +607,7 @@ int32_t col_norms(const double* A, int lda, int rows, int n, std::vector<double>
 }
 
 int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std::vector<double>& sigma,
-                   std::vector<int>& order, int* sweeps_out) {
+                   std::vector<int>& order, int* sweeps_out, bool well_scaled) {
     Ctx& cx = ctx();
     MOR_ARG(A && rows >= 1 && n >= 1 && lda >= rows, "jacobi_svd: bad arguments");
     DevBuf info_buf, norms;
@@ -632,7 +631,17 @@ int32_t jacobi_svd(double* A, int rows, int n, int lda, double* V, int ldv, std:
     while (!converged && sweeps < max_sweeps) {
         MOR_TRY(small_info_reset(d_info));
         const int big = rows > n ? rows : n;
-        if (V == nullptr && rows <= 4 * ST && n >= 16) MOR_TRY(launch_block_sweep(A, lda, rows, n, tol, d_info, ver_buf.as<int>(), sweeps));
+        // The Gram form of the round (one block-wide reduction instead of four) updates the pair block's Gram matrix
+        // algebraically inside a round.  That is accurate when the factor is a column / row scaling of a
+        // well-conditioned matrix (the one-pass path, certified by the scaled Gram test) and NOT when it is a strongly
+        // graded multi-pass factor: on the 256 x 256 core of a Burgers POD it keeps rotating on rounding noise and never
+        // meets the threshold.  So: only where the caller vouches for the scaling, and only for the first sweeps -- if
+        // it has not converged by then, the four-step form (dot products recomputed from the columns before every
+        // rotation) takes over from wherever the orthogonal transformations so far have left the columns.
+        static const bool gram_env = !(getenv("MOR_B200_JACOBI_GRAM") && getenv("MOR_B200_JACOBI_GRAM")[0] == '0');
+        const bool gram_form = well_scaled && gram_env && sweeps < 6;
+        if (V == nullptr && rows <= 4 * ST && n >= 16)
+            MOR_TRY(launch_block_sweep(A, lda, rows, n, tol, d_info, ver_buf.as<int>(), sweeps, gram_form));
         else if (big <= 4 * ST) MOR_TRY(launch_sweep<4>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));
         else if (big <= 16 * ST) MOR_TRY(launch_sweep<16>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));
         else MOR_TRY(launch_sweep<0>(A, lda, rows, V, ldv, n, n, n_even, tol, d_info));

@@ -284,7 +284,8 @@ int32_t factor_tall(mor_pod_s* h, double* T, int64_t trows, int n, int64_t ldt, 
     std::vector<int> order;
     int sweeps = 0;
     dbg.lap("copy R / deflate");
-    int32_t js = jacobi_svd(A.as<double>(), n, n, n, accumulate_v ? V.as<double>() : nullptr, n, h->sigma, order, &sweeps);
+    int32_t js = jacobi_svd(A.as<double>(), n, n, n, accumulate_v ? V.as<double>() : nullptr, n, h->sigma, order, &sweeps,
+                            /*well_scaled=*/on_transpose);
     if (js != MOR_OK) {
         tm.core.stop();
         return js;
