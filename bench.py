@@ -922,13 +922,11 @@ def run_ours(args):
             "e2e": deim_e2e}
     # ---- the "next" rows of SURVEY 8f, measured on the same basis (never fatal for the bench line) --------------------
     next_rows = None
-    if not args.no_next_rows:
+    if not args.no_next_rows and world == 1:      # the N = 1 line carries them; the scaling runs stay lean
         try:
             next_rows = next_rows_section(args, lib, B, idx, md_loc, r0d, Md, world, hbm_peak, pk_t.value)
         except Exception as ex:
             next_rows = {"error": repr(ex)}
-            if world > 1:
-                raise
     B.free()
     single = None
     if world > 1:
