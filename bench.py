@@ -11,10 +11,16 @@
 
 One "step" = one full pass of the hot path over the resident input: factorisation
 (Gram -> Cholesky -> Jacobi) + basis U_k.  `value` is device-resident (inputs in HBM when the
-timed region starts); `e2e` goes through the host-pointer C ABI (mor_b200_pod_factor +
-mor_b200_pod_basis: what the Julia shim calls) with pinned host buffers, copies inside the
-timed region.  `--impl reference` times the CPU restatement of the reference path (scipy
-OpenBLAS dgesdd = what LinearAlgebra.svd dispatches to) on a bounded row sample.
+timed region starts) and counts SURVEY 8d's algorithmic flops; `executed_tflops` is the hardware
+rate.  `e2e` goes through the host-pointer C ABI (mor_b200_pod_factor + mor_b200_pod_basis: what
+the Julia shim calls), copies inside the timed region, from page-locked buffers and (`e2e.pageable`)
+from ordinary pageable memory.  At N > 1, rank 0 afterwards repeats the e2e calls from ONE process
+driving all N GPUs (`single_process`: mor_b200_init_multi).  Correctness at full size: `checks`,
+`deim.independent_check` (torch fp64, none of the library's kernels), `rsvd.checks`, `kat`.
+`next_rows` (N = 1): the projector and Galerkin-projection rows of SURVEY 8f.
+`--impl reference` times the CPU restatement of the reference path (scipy OpenBLAS dgesdd = what
+LinearAlgebra.svd dispatches to, all host cores) on a bounded row sample and says so
+(`sample_rows`, `extrapolated`, `linearity`).
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun.
 """
